@@ -1,0 +1,156 @@
+/*
+ * surfel_rasterizer.h -- C ABI of the B200-native differentiable 2D-Gaussian surfel rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of DavidXu-JJ/StreetUnveiler: it replaces the
+ * raw-pointer layer `CudaRasterizer::Rasterizer::{forward,backward,markVisible}`
+ * (RAST/cuda_rasterizer/rasterizer.h:24-86, "RAST/" = submodules/diff-surfel-rasterization/) that
+ * the reference's torch binding (RAST/rasterize_points.cu:39,136,235; RAST/ext.cpp:15-19) calls.
+ *
+ * Differences from the reference interface, all forced by a C ABI (no std::function, no torch):
+ *   - The caller owns ALL device memory.  The three `std::function<char*(size_t)>` resize
+ *     callbacks (rasterizer.h:32-34) become size queries + a two-stage forward: stage A
+ *     (`surfel_forward_prepare`) returns num_rendered, the caller allocates the binning scratch of
+ *     `surfel_binning_bytes(num_rendered)`, stage B (`surfel_forward_render`) finishes.
+ *   - Every entry point takes the CUDA stream to launch on (the reference uses the legacy
+ *     default stream everywhere) and returns 0 on success / non-zero on failure with the message
+ *     available from `surfel_last_error()` (the reference throws std::runtime_error only when
+ *     `debug` is set, auxiliary.h:296-303; here `debug` != 0 synchronises and checks per stage).
+ *   - Gradient outputs do not need to be zero-filled by the caller (the reference binding
+ *     zero-fills 304 B/Gaussian per backward, rasterize_points.cu:187-195): every element of
+ *     every output is written by the library.
+ *
+ * All pointers are DEVICE pointers unless marked host.  All arrays are dense, row-major fp32
+ * (int32 for radii), with exactly the reference's shapes and meaning.  Matrices use the
+ * reference's layout: `viewmatrix` / `projmatrix` are the transposed (row-vector convention)
+ * world->view and full projection matrices (scene/cameras.py:61-71).
+ * A NULL pointer selects the alternative input path exactly like the reference's empty tensors:
+ * `shs` xor `colors_precomp`; (`scales`,`rotations`) xor `transMat_precomp`.
+ *
+ * The library keeps no state between calls: forward -> backward state lives in the three
+ * caller-owned scratch buffers (geometry / binning / image), whose layout is private.
+ */
+#ifndef SURFEL_RASTERIZER_H_INCLUDED
+#define SURFEL_RASTERIZER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURFEL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SURFEL_API __attribute__((visibility("default")))
+#else
+#define SURFEL_API
+#endif
+
+/* ABI version of the loaded library (== SURFEL_ABI_VERSION it was built with). */
+SURFEL_API int surfel_abi_version(void);
+
+/* Message of the last failing call on this thread ("" if none). Never NULL. */
+SURFEL_API const char *surfel_last_error(void);
+
+/*
+ * Scratch sizes.  Replace `required<GeometryState>(P)`, `required<ImageState>(W*H)`,
+ * `required<BinningState>(R)` (RAST/cuda_rasterizer/rasterizer_impl.h:67-73, used at
+ * rasterizer_impl.cu:226,239,284).  Return 0 and set the error message on failure.
+ */
+SURFEL_API size_t surfel_geometry_bytes(int P);
+SURFEL_API size_t surfel_image_bytes(int width, int height);
+SURFEL_API size_t surfel_binning_bytes(int64_t num_rendered);
+
+/*
+ * Forward, stage A  (replaces Rasterizer::forward up to the num_rendered read-back,
+ * rasterizer_impl.cu:198-282): per-Gaussian projection / tangent-frame transform / SH colour /
+ * tile-rect count, depth ordering and prefix sum.
+ *   radii          out int32[P]      (0 = culled), same values as the reference
+ *   num_rendered   out HOST int64    number of (tile, Gaussian) instances R
+ * Blocks the calling thread until R is known (the reference does the same, :282).
+ */
+SURFEL_API int surfel_forward_prepare(
+    int P, int D, int M,
+    int width, int height,
+    const float *means3D,          /* [P,3] */
+    const float *shs,              /* [P,M,3] or NULL */
+    const float *colors_precomp,   /* [P,3]   or NULL */
+    const float *opacities,        /* [P] */
+    const float *scales,           /* [P,2]   or NULL */
+    float scale_modifier,
+    const float *rotations,        /* [P,4]   or NULL */
+    const float *transMat_precomp, /* [P,9]   or NULL */
+    const float *viewmatrix,       /* [16] */
+    const float *projmatrix,       /* [16] */
+    const float *cam_pos,          /* [3] */
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    int *radii,
+    char *geometry_buffer,         /* surfel_geometry_bytes(P) */
+    int64_t *num_rendered,         /* host */
+    void *stream, int debug);
+
+/*
+ * Forward, stage B  (replaces rasterizer_impl.cu:284-342): (tile, depth) ordered instance list,
+ * per-tile ranges and the front-to-back blend.
+ *   out_color   out fp32[3,H,W]
+ *   out_others  out fp32[7,H,W]  (depth, alpha, normal xyz, median depth, distortion)
+ * Neither output needs to be initialised.
+ */
+SURFEL_API int surfel_forward_render(
+    int P, int width, int height, int64_t num_rendered,
+    const float *background,       /* [3] */
+    const int *radii,
+    char *geometry_buffer, char *binning_buffer, char *image_buffer,
+    float *out_color, float *out_others,
+    void *stream, int debug);
+
+/*
+ * Backward  (replaces Rasterizer::backward, rasterizer_impl.cu:346-448, with the reference's
+ * gradient conventions -- including its documented non-true gradients).
+ * Outputs (all fully written, no pre-zeroing needed):
+ *   dL_dmean2D [P,3], dL_dopacity [P], dL_dcolor [P,3], dL_dmean3D [P,3], dL_dtransMat [P,9],
+ *   dL_dsh [P,M,3] (ignored if M == 0 / shs NULL), dL_dscale [P,2], dL_drot [P,4]
+ * `dL_dnormal` (internal in the reference, rasterize_points.cu:190) is optional (may be NULL).
+ * `grad_scratch`: surfel_grad_scratch_bytes(P) bytes of device scratch.
+ */
+SURFEL_API size_t surfel_grad_scratch_bytes(int P);
+SURFEL_API int surfel_backward(
+    int P, int D, int M, int64_t num_rendered,
+    const float *background,
+    int width, int height,
+    const float *means3D, const float *shs, const float *colors_precomp,
+    const float *scales, float scale_modifier, const float *rotations,
+    const float *transMat_precomp,
+    const float *viewmatrix, const float *projmatrix, const float *cam_pos,
+    float tan_fovx, float tan_fovy,
+    const int *radii,
+    char *geometry_buffer, char *binning_buffer, char *image_buffer,
+    const float *dL_dpix,          /* [3,H,W] */
+    const float *dL_dothers,       /* [7,H,W] */
+    float *dL_dmean2D, float *dL_dnormal, float *dL_dopacity, float *dL_dcolor,
+    float *dL_dmean3D, float *dL_dtransMat, float *dL_dsh, float *dL_dscale, float *dL_drot,
+    char *grad_scratch,
+    void *stream, int debug);
+
+/* Replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153): present[i] = view_z > 0.2 */
+SURFEL_API int surfel_mark_visible(int P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                        unsigned char *present, void *stream);
+
+/*
+ * Debug views into the private scratch layout (used only by the exact-equality tests):
+ * copies the per-tile ranges [tiles,2] (uint32) and the sorted instance list [R] (uint32 Gaussian
+ * ids) into caller-provided DEVICE buffers.
+ */
+SURFEL_API int surfel_debug_copy_binning(int width, int height, int64_t num_rendered,
+                              const char *binning_buffer, const char *image_buffer,
+                              uint32_t *ranges_out, uint32_t *point_list_out, void *stream);
+
+/* Tuning / debug knobs: "subtile_cull" (default 1). Returns 0 if the option exists. */
+SURFEL_API int surfel_set_option(const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFEL_RASTERIZER_H_INCLUDED */

@@ -1,0 +1,79 @@
+"""ctypes loader of libsurfel_b200.so (C ABI: include/surfel_rasterizer.h).
+
+The product path has NO fallback: if the CUDA library is missing or a call fails, a RuntimeError
+is raised.  Nothing here imports or executes oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsurfel_b200.so")
+ABI_VERSION = 1
+
+_lib = None
+
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> (restype, argtypes): every symbol declared in include/surfel_rasterizer.h
+SIGNATURES = {
+    "surfel_abi_version": (_i, []),
+    "surfel_last_error": (C.c_char_p, []),
+    "surfel_geometry_bytes": (C.c_size_t, [_i]),
+    "surfel_image_bytes": (C.c_size_t, [_i, _i]),
+    "surfel_binning_bytes": (C.c_size_t, [_i64]),
+    "surfel_grad_scratch_bytes": (C.c_size_t, [_i]),
+    "surfel_forward_prepare": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f,
+                                    _i, _vp, _vp, C.POINTER(_i64), _vp, _i]),
+    "surfel_forward_render": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "surfel_backward": (_i, [_i, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f,
+                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "surfel_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_debug_copy_binning": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_set_option": (_i, [C.c_char_p, _i]),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    import subprocess
+
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("building libsurfel_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C streetunveiler_b200/csrc`). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if L.surfel_abi_version() != ABI_VERSION:
+            raise RuntimeError("libsurfel_b200.so ABI version mismatch; rebuild it")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().surfel_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def size(n: int, what: str) -> int:
+    if n == 0:
+        msg = lib().surfel_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed: {msg}")
+    return int(n)

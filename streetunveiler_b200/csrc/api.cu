@@ -1,0 +1,331 @@
+// api.cu -- extern "C" boundary (include/surfel_rasterizer.h) and host orchestration.
+//
+// Mirrors the raw-pointer layer CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// (RAST/cuda_rasterizer/rasterizer.h:24-86; orchestration rasterizer_impl.cu:198-342,346-448)
+// with caller-owned memory, an explicit stream and int error codes.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/surfel_rasterizer.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace surfel;
+
+namespace {
+
+thread_local std::string g_err;
+int g_subtile_cull = 1;
+
+int fail(const char *where, const char *what)
+{
+    g_err = std::string(where) + ": " + what;
+    return 1;
+}
+int fail_cuda(const char *where, cudaError_t e)
+{
+    g_err = std::string(where) + ": CUDA error: " + cudaGetErrorString(e);
+    return 2;
+}
+
+#define CK(where, expr)                                    \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) return fail_cuda(where, _e); \
+    } while (0)
+
+// debug: synchronise + surface asynchronous errors after every stage (reference CHECK_CUDA, auxiliary.h:296-303)
+#define STAGE(where)                                                   \
+    do {                                                               \
+        cudaError_t _e = cudaGetLastError();                           \
+        if (_e == cudaSuccess && debug) _e = cudaStreamSynchronize(st); \
+        if (_e != cudaSuccess) return fail_cuda(where, _e);            \
+    } while (0)
+
+GeomView carve_geom(char *base, int P, size_t cub_bytes)
+{
+    GeomView g;
+    char *p = base;
+    const size_t n = (size_t)(P > 0 ? P : 1);
+    g.rec = carve<float>(p, n * REC_FLOATS);
+    g.tiles_touched = carve<uint32_t>(p, n);
+    g.depth_key = carve<uint32_t>(p, n);
+    g.depth_key_sorted = carve<uint32_t>(p, n);
+    g.idx_in = carve<uint32_t>(p, n);
+    g.idx_sorted = carve<uint32_t>(p, n);
+    g.offsets = carve<uint32_t>(p, n);
+    g.clamped = carve<uint8_t>(p, n);
+    g.num_rendered = carve<int64_t>(p, 1);
+    g.cub_temp = carve<char>(p, cub_bytes);
+    g.cub_temp_bytes = cub_bytes;
+    return g;
+}
+size_t geom_end(int P, size_t cub_bytes)
+{
+    GeomView g = carve_geom(nullptr, P, cub_bytes);
+    return (size_t)(g.cub_temp + cub_bytes) + 128;
+}
+
+ImageView carve_image(char *base, int W, int H)
+{
+    ImageView v;
+    char *p = base;
+    const size_t HW = (size_t)W * H;
+    const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+    v.ranges = carve<uint2>(p, tiles);
+    v.final_T = carve<float>(p, 3 * HW);
+    v.n_contrib = carve<uint32_t>(p, 2 * HW);
+    v.tile_max_contrib = carve<uint32_t>(p, tiles);
+    return v;
+}
+
+BinView carve_bin(char *base, int64_t R, size_t cub_bytes)
+{
+    BinView b;
+    char *p = base;
+    const size_t n = (size_t)(R > 0 ? R : 1);
+    b.keys_unsorted = carve<uint32_t>(p, n);
+    b.vals_unsorted = carve<uint32_t>(p, n);
+    b.keys_sorted = carve<uint32_t>(p, n);
+    b.point_list = carve<uint32_t>(p, n);
+    b.cub_temp = carve<char>(p, cub_bytes);
+    b.cub_temp_bytes = cub_bytes;
+    return b;
+}
+
+bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+bool have_device()
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int surfel_abi_version(void) { return SURFEL_ABI_VERSION; }
+
+const char *surfel_last_error(void) { return g_err.c_str(); }
+
+int surfel_set_option(const char *name, int value)
+{
+    if (name && std::strcmp(name, "subtile_cull") == 0) {
+        g_subtile_cull = value;
+        return 0;
+    }
+    return fail("surfel_set_option", "unknown option");
+}
+
+size_t surfel_geometry_bytes(int P)
+{
+    if (P < 0) { fail("surfel_geometry_bytes", "negative P"); return 0; }
+    if (!have_device()) { fail("surfel_geometry_bytes", "no CUDA device (this library has no CPU path)"); return 0; }
+    return geom_end(P, depth_sort_temp_bytes(P));
+}
+
+size_t surfel_image_bytes(int width, int height)
+{
+    if (width <= 0 || height <= 0) { fail("surfel_image_bytes", "bad image size"); return 0; }
+    ImageView v = carve_image(nullptr, width, height);
+    const size_t tiles = (size_t)((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
+    return (size_t)(v.tile_max_contrib + tiles) + 128;
+}
+
+size_t surfel_binning_bytes(int64_t num_rendered)
+{
+    if (num_rendered < 0) { fail("surfel_binning_bytes", "negative num_rendered"); return 0; }
+    if (!have_device()) { fail("surfel_binning_bytes", "no CUDA device (this library has no CPU path)"); return 0; }
+    const size_t cub = tile_sort_temp_bytes(num_rendered);
+    BinView b = carve_bin(nullptr, num_rendered, cub);
+    return (size_t)(b.cub_temp + cub) + 128;
+}
+
+size_t surfel_grad_scratch_bytes(int P)
+{
+    if (P < 0) { fail("surfel_grad_scratch_bytes", "negative P"); return 0; }
+    return (size_t)(P > 0 ? P : 1) * GACC_FLOATS * sizeof(float) + 128;
+}
+
+int surfel_forward_prepare(int P, int D, int M, int width, int height, const float *means3D, const float *shs,
+                           const float *colors_precomp, const float *opacities, const float *scales,
+                           float scale_modifier, const float *rotations, const float *transMat_precomp,
+                           const float *viewmatrix, const float *projmatrix, const float *cam_pos, float tan_fovx,
+                           float tan_fovy, int prefiltered, int *radii, char *geometry_buffer,
+                           int64_t *num_rendered, void *stream, int debug)
+{
+    (void)tan_fovx; (void)tan_fovy;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!num_rendered) return fail("surfel_forward_prepare", "num_rendered is NULL");
+    *num_rendered = 0;
+    if (P < 0 || width <= 0 || height <= 0) return fail("surfel_forward_prepare", "bad sizes");
+    if (P == 0) return 0;
+    if (!means3D || !opacities || !viewmatrix || !projmatrix || !cam_pos || !radii || !geometry_buffer)
+        return fail("surfel_forward_prepare", "NULL required pointer");
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+        return fail("surfel_forward_prepare", "provide exactly one of shs / colors_precomp");
+    if (shs && (M <= 0 || D < 0 || D > 3 || (D + 1) * (D + 1) > M))
+        return fail("surfel_forward_prepare", "SH degree / coefficient count mismatch");
+    const bool have_sr = scales != nullptr && rotations != nullptr;
+    if (have_sr == (transMat_precomp != nullptr) || ((scales == nullptr) != (rotations == nullptr)))
+        return fail("surfel_forward_prepare", "provide exactly one of (scales, rotations) / transMat_precomp");
+    if (have_sr && (!aligned(scales, 8) || !aligned(rotations, 16)))
+        return fail("surfel_forward_prepare", "scales must be 8-byte and rotations 16-byte aligned");
+    if (!aligned(geometry_buffer, 16)) return fail("surfel_forward_prepare", "geometry_buffer must be 16-byte aligned");
+
+    const size_t cub = depth_sort_temp_bytes(P);
+    GeomView g = carve_geom(geometry_buffer, P, cub);
+
+    PreprocessFwdArgs a;
+    a.P = P; a.D = D; a.M = M; a.W = width; a.H = height;
+    a.gx = (width + TILE_X - 1) / TILE_X; a.gy = (height + TILE_Y - 1) / TILE_Y;
+    a.prefiltered = prefiltered; a.scale_modifier = scale_modifier;
+    a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.opacities = opacities; a.shs = shs;
+    a.transMat_precomp = transMat_precomp; a.colors_precomp = colors_precomp;
+    a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+    a.radii = radii; a.rec = g.rec; a.tiles_touched = g.tiles_touched; a.depth_key = g.depth_key;
+    a.idx_in = g.idx_in; a.clamped = g.clamped;
+    launch_preprocess_fwd(a, st);
+    STAGE("preprocess");
+
+    CK("depth order", run_depth_order(P, g.depth_key, g.depth_key_sorted, g.idx_in, g.idx_sorted, g.tiles_touched,
+                                      g.offsets, g.num_rendered, g.cub_temp, g.cub_temp_bytes, st));
+    STAGE("depth order");
+
+    uint32_t r32 = 0;
+    CK("num_rendered readback", cudaMemcpyAsync(&r32, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK("num_rendered readback", cudaStreamSynchronize(st));
+    *num_rendered = (int64_t)r32;
+    return 0;
+}
+
+int surfel_forward_render(int P, int width, int height, int64_t num_rendered, const float *background,
+                          const int *radii, char *geometry_buffer, char *binning_buffer, char *image_buffer,
+                          float *out_color, float *out_others, void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail("surfel_forward_render", "bad sizes");
+    if (!background || !image_buffer || !out_color || !out_others)
+        return fail("surfel_forward_render", "NULL required pointer");
+    if (P > 0 && (!radii || !geometry_buffer)) return fail("surfel_forward_render", "NULL geometry");
+    if (num_rendered > 0 && !binning_buffer) return fail("surfel_forward_render", "NULL binning_buffer");
+
+    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    ImageView iv = carve_image(image_buffer, width, height);
+    GeomView g{};
+    BinView bv{};
+    if (P > 0) g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    if (num_rendered > 0) {
+        const size_t cub = tile_sort_temp_bytes(num_rendered);
+        bv = carve_bin(binning_buffer, num_rendered, cub);
+    }
+    CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, g.rec, radii, g.idx_sorted, g.offsets,
+                                        bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted, bv.point_list, iv.ranges,
+                                        bv.cub_temp, bv.cub_temp_bytes, st));
+    STAGE("tile binning");
+
+    RenderFwdArgs r;
+    r.W = width; r.H = height; r.gx = gx; r.gy = gy;
+    r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
+    r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
+    r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
+    launch_render_fwd(r, st);
+    STAGE("render forward");
+    return 0;
+}
+
+int surfel_backward(int P, int D, int M, int64_t num_rendered, const float *background, int width, int height,
+                    const float *means3D, const float *shs, const float *colors_precomp, const float *scales,
+                    float scale_modifier, const float *rotations, const float *transMat_precomp,
+                    const float *viewmatrix, const float *projmatrix, const float *cam_pos, float tan_fovx,
+                    float tan_fovy, const int *radii, char *geometry_buffer, char *binning_buffer,
+                    char *image_buffer, const float *dL_dpix, const float *dL_dothers, float *dL_dmean2D,
+                    float *dL_dnormal, float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D, float *dL_dtransMat,
+                    float *dL_dsh, float *dL_dscale, float *dL_drot, char *grad_scratch, void *stream, int debug)
+{
+    (void)scale_modifier; (void)colors_precomp;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail("surfel_backward", "bad sizes");
+    if (P == 0) return 0;
+    if (!background || !means3D || !viewmatrix || !projmatrix || !cam_pos || !radii || !geometry_buffer ||
+        !image_buffer || !dL_dpix || !dL_dothers || !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D ||
+        !dL_dtransMat || !dL_dscale || !dL_drot || !grad_scratch)
+        return fail("surfel_backward", "NULL required pointer");
+    if (shs && M > 0 && !dL_dsh) return fail("surfel_backward", "dL_dsh is NULL but shs given");
+    if (num_rendered > 0 && !binning_buffer) return fail("surfel_backward", "NULL binning_buffer");
+    if ((scales == nullptr) != (rotations == nullptr) || ((scales == nullptr) && !transMat_precomp))
+        return fail("surfel_backward", "provide (scales, rotations) or transMat_precomp");
+    if (!aligned(dL_dscale, 8) || !aligned(dL_drot, 16) || (scales && (!aligned(scales, 8) || !aligned(rotations, 16))))
+        return fail("surfel_backward", "scale/rotation buffers must be 8/16-byte aligned");
+
+    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    GeomView g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    ImageView iv = carve_image(image_buffer, width, height);
+    BinView bv{};
+    if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
+
+    char *gp = grad_scratch;
+    float *gacc = carve<float>(gp, (size_t)P * GACC_FLOATS);
+    CK("grad scratch clear", cudaMemsetAsync(gacc, 0, (size_t)P * GACC_FLOATS * sizeof(float), st));
+
+    if (num_rendered > 0) {
+        RenderBwdArgs r;
+        r.W = width; r.H = height; r.gx = gx; r.gy = gy;
+        r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
+        r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
+        r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = gacc; r.subtile_cull = g_subtile_cull;
+        launch_render_bwd(r, st);
+        STAGE("render backward");
+    }
+
+    PreprocessBwdArgs a;
+    a.P = P; a.D = D; a.M = M;
+    a.focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:388-389
+    a.focal_x = width / (2.0f * tan_fovx);
+    a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+    a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
+    a.transMat_precomp = transMat_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+    a.radii = radii; a.clamped = g.clamped; a.rec = g.rec; a.gacc = gacc;
+    a.dL_dmean2D = dL_dmean2D; a.dL_dnormal = dL_dnormal; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
+    a.dL_dmean3D = dL_dmean3D; a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale;
+    a.dL_drot = dL_drot;
+    launch_preprocess_bwd(a, st);
+    STAGE("preprocess backward");
+    return 0;
+}
+
+int surfel_mark_visible(int P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                        unsigned char *present, void *stream)
+{
+    (void)projmatrix;
+    if (P < 0) return fail("surfel_mark_visible", "negative P");
+    if (P == 0) return 0;
+    if (!means3D || !viewmatrix || !present) return fail("surfel_mark_visible", "NULL required pointer");
+    launch_mark_visible(P, means3D, viewmatrix, present, static_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda("surfel_mark_visible", e);
+    return 0;
+}
+
+int surfel_debug_copy_binning(int width, int height, int64_t num_rendered, const char *binning_buffer,
+                              const char *image_buffer, uint32_t *ranges_out, uint32_t *point_list_out, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (width <= 0 || height <= 0 || num_rendered < 0 || !image_buffer)
+        return fail("surfel_debug_copy_binning", "bad arguments");
+    const size_t tiles = (size_t)((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
+    ImageView iv = carve_image(const_cast<char *>(image_buffer), width, height);
+    if (ranges_out)
+        CK("copy ranges", cudaMemcpyAsync(ranges_out, iv.ranges, tiles * sizeof(uint2), cudaMemcpyDeviceToDevice, st));
+    if (point_list_out && num_rendered > 0) {
+        if (!binning_buffer) return fail("surfel_debug_copy_binning", "NULL binning_buffer");
+        BinView bv = carve_bin(const_cast<char *>(binning_buffer), num_rendered, tile_sort_temp_bytes(num_rendered));
+        CK("copy point list", cudaMemcpyAsync(point_list_out, bv.point_list, (size_t)num_rendered * sizeof(uint32_t),
+                                              cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// kernels.h -- host-side launch interfaces between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace surfel {
+
+struct PreprocessFwdArgs {
+    int P, D, M, W, H, gx, gy, prefiltered;
+    float scale_modifier;
+    const float *means3D, *scales, *rotations, *opacities, *shs, *transMat_precomp, *colors_precomp;
+    const float *viewmatrix, *projmatrix, *cam_pos;
+    int *radii;
+    float *rec;
+    uint32_t *tiles_touched, *depth_key, *idx_in;
+    uint8_t *clamped;
+};
+void launch_preprocess_fwd(const PreprocessFwdArgs &a, cudaStream_t stream);
+void launch_mark_visible(int P, const float *means3D, const float *viewmatrix, unsigned char *present,
+                         cudaStream_t stream);
+
+struct PreprocessBwdArgs {
+    int P, D, M;
+    float focal_x, focal_y, tan_fovx, tan_fovy;
+    const float *means3D, *shs, *scales, *rotations, *transMat_precomp, *viewmatrix, *projmatrix, *cam_pos;
+    const int *radii;
+    const uint8_t *clamped;
+    const float *rec, *gacc;
+    float *dL_dmean2D, *dL_dnormal, *dL_dopacity, *dL_dcolor, *dL_dmean3D, *dL_dtransMat, *dL_dsh, *dL_dscale,
+        *dL_drot;
+};
+void launch_preprocess_bwd(const PreprocessBwdArgs &a, cudaStream_t stream);
+
+// ---- binning (binning.cu) ----
+size_t depth_sort_temp_bytes(int P);
+size_t tile_sort_temp_bytes(int64_t R);
+// depth-order the Gaussians, scan tiles_touched in that order, leave R in *num_rendered_dev
+cudaError_t run_depth_order(int P, const uint32_t *depth_key, uint32_t *depth_key_sorted, const uint32_t *idx_in,
+                            uint32_t *idx_sorted, const uint32_t *tiles_touched, uint32_t *offsets,
+                            int64_t *num_rendered_dev, char *temp, size_t temp_bytes, cudaStream_t stream);
+// emit (tile, id) pairs in depth order, stable-sort by tile, find per-tile ranges
+cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, const float *rec, const int *radii,
+                             const uint32_t *idx_sorted, const uint32_t *offsets, uint32_t *keys_unsorted,
+                             uint32_t *vals_unsorted, uint32_t *keys_sorted, uint32_t *point_list, uint2 *ranges,
+                             char *temp, size_t temp_bytes, cudaStream_t stream);
+
+// ---- render (render_fwd.cu / render_bwd.cu) ----
+struct RenderFwdArgs {
+    int W, H, gx, gy;
+    const uint2 *ranges;
+    const uint32_t *point_list;
+    const float *rec;
+    const float *bg;
+    float *final_T;
+    uint32_t *n_contrib;
+    uint32_t *tile_max_contrib;
+    float *out_color, *out_others;
+    int subtile_cull;
+};
+void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream);
+
+struct RenderBwdArgs {
+    int W, H, gx, gy;
+    const uint2 *ranges;
+    const uint32_t *point_list;
+    const float *rec;
+    const float *bg;
+    const float *final_T;
+    const uint32_t *n_contrib;
+    const uint32_t *tile_max_contrib;
+    const float *dL_dpix, *dL_dothers;
+    float *gacc;  // [P][GACC_FLOATS], zero-initialised by the caller of the launch
+    int subtile_cull;
+};
+void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream);
+
+}  // namespace surfel

@@ -1,0 +1,622 @@
+// preprocess.cu -- per-Gaussian forward projection (K1) and per-Gaussian backward (K8).
+//
+// Behavioural specification (reference, "RAST/" = submodules/diff-surfel-rasterization/):
+//   forward : RAST/cuda_rasterizer/forward.cu:148-251 (preprocessCUDA), :75-115 (compute_transmat),
+//             :119-145 (compute_aabb), :20-71 (computeColorFromSH), auxiliary.h:67-77,185-235
+//   backward: RAST/cuda_rasterizer/backward.cu:581-636 (preprocessCUDA), :449-579
+//             (compute_transmat_aabb), :20-139 (SH VJP), auxiliary.h:128-138,238-282
+//
+// The arithmetic keeps the reference's operation order (including glm's column-major product
+// order) because radii / tile rects / sort keys must come out bit-identical; the memory side is
+// new: one thread per Gaussian, 128-bit loads of rotation / SH rows, and ONE packed 80-B record
+// per Gaussian (common.cuh) instead of six separate arrays, plus a conservative alpha>=1/255
+// pixel bounding box used by the render kernels for sub-tile culling.
+#include <cstdio>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace surfel {
+
+__device__ __constant__ float kSH_C0 = 0.28209479177387814f;
+__device__ __constant__ float kSH_C1 = 0.4886025119029199f;
+__device__ __constant__ float kSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                           -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                           0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                           -0.5900435899266435f};
+
+// Rotation matrix columns from a (w,x,y,z) quaternion, normalised in-kernel (auxiliary.h:213-235).
+__device__ __forceinline__ void quat_columns(const float4 q, float R[3][3])
+{
+    const float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    const float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
+    R[0][0] = 1.f - 2.f * (y * y + z * z);
+    R[0][1] = 2.f * (x * y + w * z);
+    R[0][2] = 2.f * (x * z - w * y);
+    R[1][0] = 2.f * (x * y - w * z);
+    R[1][1] = 1.f - 2.f * (x * x + z * z);
+    R[1][2] = 2.f * (y * z + w * x);
+    R[2][0] = 2.f * (x * z + w * y);
+    R[2][1] = 2.f * (y * z - w * x);
+    R[2][2] = 1.f - 2.f * (x * x + y * y);
+}
+
+// L = R * diag(sx, sy, 1) in glm's accumulation order (type_mat3x3.inl operator*).
+__device__ __forceinline__ void scaled_frame(const float R[3][3], float sx, float sy, float L[3][3])
+{
+    const float S[3][3] = {{sx, 0.f, 0.f}, {0.f, sy, 0.f}, {0.f, 0.f, 1.f}};
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) L[c][r] = R[0][r] * S[c][0] + R[1][r] * S[c][1] + R[2][r] * S[c][2];
+}
+
+__device__ __forceinline__ float3 xform_point(const float3 p, const float *m)
+{
+    return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ float3 xform_vec(const float3 p, const float *m)
+{
+    return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z, m[1] * p.x + m[5] * p.y + m[9] * p.z,
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z);
+}
+__device__ __forceinline__ float3 xform_vec_transposed(const float3 p, const float *m)
+{
+    return make_float3(m[0] * p.x + m[1] * p.y + m[2] * p.z, m[4] * p.x + m[5] * p.y + m[6] * p.z,
+                       m[8] * p.x + m[9] * p.y + m[10] * p.z);
+}
+
+__device__ __forceinline__ float dot3(const float a0, const float a1, const float a2, const float b0, const float b1,
+                                      const float b2)
+{
+    const float t0 = a0 * b0, t1 = a1 * b1, t2 = a2 * b2;
+    return t0 + t1 + t2;
+}
+
+// Tile rectangle of a splat (auxiliary.h:67-77): int truncation of float quotients, clamped.
+__device__ __forceinline__ void tile_rect(const float px, const float py, const int max_radius, const int gx,
+                                          const int gy, int &x0, int &y0, int &x1, int &y1)
+{
+    x0 = min(gx, max(0, (int)((px - max_radius) / TILE_X)));
+    y0 = min(gy, max(0, (int)((py - max_radius) / TILE_Y)));
+    x1 = min(gx, max(0, (int)((px + max_radius + TILE_X - 1) / TILE_X)));
+    y1 = min(gy, max(0, (int)((py + max_radius + TILE_Y - 1) / TILE_Y)));
+}
+
+// Conservative inclusive pixel bounds of the region where this splat can reach alpha >= 1/255
+// (rho = min(rho3d, rho2d) <= tau = 2 ln(255 o)); margins absorb fp32 rounding of the conic AABB.
+__device__ __forceinline__ void alpha_bbox(const float Tm[3][3], const float mx, const float my, const float opacity,
+                                           const int W, const int H, uint32_t &bx, uint32_t &by)
+{
+    int x0 = 0, x1 = W - 1, y0 = 0, y1 = H - 1;
+    const float o255 = 255.0f * opacity;
+    if (!(o255 >= 1.0f)) {
+        // o * exp(<=0) < 1/255 for every pixel unless rounding interferes: keep a 1-ulp guard
+        if (o255 < 0.999f) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }
+    } else {
+        const float tau = 2.0f * __logf(o255) * 1.002f + 0.01f;
+        // low-pass disc: 2 |d|^2 <= tau
+        const float rl = sqrtf(0.5f * tau) + 0.5f;
+        float lx = mx - rl, hx = mx + rl, ly = my - rl, hy = my + rl;
+        // perspective-correct ellipse u^2+v^2 <= tau: same conic AABB as forward.cu:119-145 with cutoff^2 = tau
+        const float tz2 = Tm[2][2] * Tm[2][2];
+        const float d = tau * (Tm[2][0] * Tm[2][0] + Tm[2][1] * Tm[2][1]) - tz2;
+        bool bounded = d < -1e-3f * tz2;
+        if (bounded) {
+            const float inv = 1.0f / d;
+            const float f0 = tau * inv, f1 = tau * inv, f2 = -inv;
+            const float cx = f0 * Tm[0][0] * Tm[2][0] + f1 * Tm[0][1] * Tm[2][1] + f2 * Tm[0][2] * Tm[2][2];
+            const float cy = f0 * Tm[1][0] * Tm[2][0] + f1 * Tm[1][1] * Tm[2][1] + f2 * Tm[1][2] * Tm[2][2];
+            const float qx = f0 * Tm[0][0] * Tm[0][0] + f1 * Tm[0][1] * Tm[0][1] + f2 * Tm[0][2] * Tm[0][2];
+            const float qy = f0 * Tm[1][0] * Tm[1][0] + f1 * Tm[1][1] * Tm[1][1] + f2 * Tm[1][2] * Tm[1][2];
+            const float hx2 = cx * cx - qx, hy2 = cy * cy - qy;
+            if (hx2 == hx2 && hy2 == hy2 && fabsf(cx) < 1e7f && fabsf(cy) < 1e7f) {
+                // fp32 cancellation in c^2 - q: |error| <= ~1e-6 (c^2 + |q|); plus relative and absolute slack
+                const float sx2 = 1e-6f * (cx * cx + fabsf(qx)), sy2 = 1e-6f * (cy * cy + fabsf(qy));
+                const float ex = sqrtf(fmaxf(hx2 + sx2, 0.f)) * 1.002f + 0.75f;
+                const float ey = sqrtf(fmaxf(hy2 + sy2, 0.f)) * 1.002f + 0.75f;
+                lx = fminf(lx, cx - ex); hx = fmaxf(hx, cx + ex);
+                ly = fminf(ly, cy - ey); hy = fmaxf(hy, cy + ey);
+            } else {
+                bounded = false;
+            }
+        }
+        if (bounded) {
+            x0 = (int)fmaxf(floorf(lx), 0.f);
+            y0 = (int)fmaxf(floorf(ly), 0.f);
+            x1 = (int)fminf(ceilf(hx), (float)(W - 1));
+            y1 = (int)fminf(ceilf(hy), (float)(H - 1));
+            if (x1 < x0 || y1 < y0) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }
+        }
+    }
+    x0 = min(x0, 65535); x1 = min(x1, 65535); y0 = min(y0, 65535); y1 = min(y1, 65535);
+    bx = (uint32_t)x0 | ((uint32_t)x1 << 16);
+    by = (uint32_t)y0 | ((uint32_t)y1 << 16);
+}
+
+// =============================================================================================
+// K1: forward preprocess
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+preprocess_fwd_kernel(const int P, const int D, const int M, const float *__restrict__ means3D,
+                      const float2 *__restrict__ scales, const float scale_modifier,
+                      const float4 *__restrict__ rotations, const float *__restrict__ opacities,
+                      const float *__restrict__ shs, const float *__restrict__ transMat_precomp,
+                      const float *__restrict__ colors_precomp, const float *__restrict__ viewmatrix,
+                      const float *__restrict__ projmatrix, const float *__restrict__ cam_pos, const int W,
+                      const int H, const int gx, const int gy, int *__restrict__ radii, float *__restrict__ rec,
+                      uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ depth_key,
+                      uint32_t *__restrict__ idx_in, uint8_t *__restrict__ clamped, const int prefiltered)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+
+    int radius_out = 0;
+    uint32_t tiles_out = 0;
+    uint32_t key_out = 0xFFFFFFFFu;
+
+    const float3 p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    const float3 p_view = xform_point(p_orig, viewmatrix);
+
+    do {
+        if (p_view.z <= 0.2f) {  // auxiliary.h:199
+            if (prefiltered) {
+                printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+                __trap();
+            }
+            break;
+        }
+        float Tm[3][3];  // Tm[0] = Tu, Tm[1] = Tv, Tm[2] = Tw
+        float3 normal;
+        if (transMat_precomp == nullptr) {
+            float R[3][3], L[3][3];
+            const float2 sc = scales[idx];
+            quat_columns(rotations[idx], R);
+            scaled_frame(R, scale_modifier * sc.x, scale_modifier * sc.y, L);
+            // A = transpose(splat2world): columns (L0[k], L1[k], p[k]) and (0,0,1)
+            const float A[4][3] = {{L[0][0], L[1][0], p_orig.x}, {L[0][1], L[1][1], p_orig.y},
+                                   {L[0][2], L[1][2], p_orig.z}, {0.f, 0.f, 1.f}};
+            float B[4][3];  // A * world2ndc, world2ndc[c][k] = projmatrix[c + 4k]
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    B[c][r] = A[0][r] * projmatrix[c] + A[1][r] * projmatrix[c + 4] + A[2][r] * projmatrix[c + 8] +
+                              A[3][r] * projmatrix[c + 12];
+            const float N[3][4] = {{float(W) / 2.0f, 0.f, 0.f, float(W - 1) / 2.0f},
+                                   {0.f, float(H) / 2.0f, 0.f, float(H - 1) / 2.0f},
+                                   {0.f, 0.f, 0.f, 1.f}};
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    Tm[j][r] = B[0][r] * N[j][0] + B[1][r] * N[j][1] + B[2][r] * N[j][2] + B[3][r] * N[j][3];
+            normal = xform_vec(make_float3(L[2][0], L[2][1], L[2][2]), viewmatrix);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) Tm[j][r] = transMat_precomp[9 * idx + 3 * j + r];
+            normal = make_float3(0.f, 0.f, 1.f);
+        }
+
+        // dual-visible flip (forward.cu:209-214)
+        const float cosv = -(p_view.x * normal.x + p_view.y * normal.y + p_view.z * normal.z);
+        if (cosv == 0) break;
+        const float mult = cosv > 0 ? 1.f : -1.f;
+        normal = make_float3(mult * normal.x, mult * normal.y, mult * normal.z);
+
+        // centre + extent at cutoff 3 (forward.cu:119-145)
+        const float t0 = 3.0f * 3.0f, t1 = 3.0f * 3.0f, t2 = -1.0f;
+        const float d = dot3(t0, t1, t2, Tm[2][0] * Tm[2][0], Tm[2][1] * Tm[2][1], Tm[2][2] * Tm[2][2]);
+        if (d == 0.0f) break;
+        const float invd = 1 / d;
+        const float f0 = invd * t0, f1 = invd * t1, f2 = invd * t2;
+        const float cx = dot3(f0, f1, f2, Tm[0][0] * Tm[2][0], Tm[0][1] * Tm[2][1], Tm[0][2] * Tm[2][2]);
+        const float cy = dot3(f0, f1, f2, Tm[1][0] * Tm[2][0], Tm[1][1] * Tm[2][1], Tm[1][2] * Tm[2][2]);
+        const float h0x = cx * cx - dot3(f0, f1, f2, Tm[0][0] * Tm[0][0], Tm[0][1] * Tm[0][1], Tm[0][2] * Tm[0][2]);
+        const float h0y = cy * cy - dot3(f0, f1, f2, Tm[1][0] * Tm[1][0], Tm[1][1] * Tm[1][1], Tm[1][2] * Tm[1][2]);
+        const float ex = sqrtf((1e-4f < h0x) ? h0x : 1e-4f);
+        const float ey = sqrtf((1e-4f < h0y) ? h0y : 1e-4f);
+        const float radius = ceilf(fmaxf(fmaxf(ex, ey), 3.0f * FILTER_SIZE));
+
+        int rx0, ry0, rx1, ry1;
+        tile_rect(cx, cy, (int)radius, gx, gy, rx0, ry0, rx1, ry1);
+        if ((rx1 - rx0) * (ry1 - ry0) == 0) break;
+
+        // colour (forward.cu:20-71)
+        float rgb[3];
+        uint32_t clamp_bits = 0;
+        if (colors_precomp == nullptr) {
+            const float3 cam = make_float3(cam_pos[0], cam_pos[1], cam_pos[2]);
+            float dx = p_orig.x - cam.x, dy = p_orig.y - cam.y, dz = p_orig.z - cam.z;
+            const float len = sqrtf(dot3(dx, dy, dz, dx, dy, dz));
+            const float x = dx / len, y = dy / len, z = dz / len;
+            // the SH row of one Gaussian is 12*M bytes, 16-B aligned whenever M is a multiple of 4
+            float sh[48];
+            const float *row = shs + (size_t)idx * M * 3;
+            const int ncoef = (D + 1) * (D + 1);
+            if ((M & 3) == 0) {
+                const float4 *row4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+                for (int i = 0; i < 12; i++)
+                    if (i * 4 < ncoef * 3) {
+                        const float4 v = __ldg(row4 + i);
+                        sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 48; i++)
+                    if (i < ncoef * 3) sh[i] = __ldg(row + i);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+#define SHC(k) sh[3 * (k) + c]
+                float res = kSH_C0 * SHC(0);
+                if (D > 0) {
+                    res = res - kSH_C1 * y * SHC(1) + kSH_C1 * z * SHC(2) - kSH_C1 * x * SHC(3);
+                    if (D > 1) {
+                        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                        res = res + kSH_C2[0] * xy * SHC(4) + kSH_C2[1] * yz * SHC(5) +
+                              kSH_C2[2] * (2.0f * zz - xx - yy) * SHC(6) + kSH_C2[3] * xz * SHC(7) +
+                              kSH_C2[4] * (xx - yy) * SHC(8);
+                        if (D > 2) {
+                            res = res + kSH_C3[0] * y * (3.0f * xx - yy) * SHC(9) + kSH_C3[1] * xy * z * SHC(10) +
+                                  kSH_C3[2] * y * (4.0f * zz - xx - yy) * SHC(11) +
+                                  kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHC(12) +
+                                  kSH_C3[4] * x * (4.0f * zz - xx - yy) * SHC(13) + kSH_C3[5] * z * (xx - yy) * SHC(14) +
+                                  kSH_C3[6] * x * (xx - 3.0f * yy) * SHC(15);
+                        }
+                    }
+                }
+#undef SHC
+                res += 0.5f;
+                if (res < 0) clamp_bits |= (1u << c);
+                rgb[c] = fmaxf(res, 0.0f);
+            }
+        } else {
+            rgb[0] = colors_precomp[3 * idx];
+            rgb[1] = colors_precomp[3 * idx + 1];
+            rgb[2] = colors_precomp[3 * idx + 2];
+        }
+
+        const float opacity = opacities[idx];
+        uint32_t bx, by;
+        alpha_bbox(Tm, cx, cy, opacity, W, H, bx, by);
+
+        float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)idx * REC_FLOATS);
+        r4[0] = make_float4(Tm[0][0], Tm[0][1], Tm[0][2], Tm[1][0]);
+        r4[1] = make_float4(Tm[1][1], Tm[1][2], Tm[2][0], Tm[2][1]);
+        r4[2] = make_float4(Tm[2][2], cx, cy, opacity);
+        r4[3] = make_float4(normal.x, normal.y, normal.z, rgb[0]);
+        r4[4] = make_float4(rgb[1], rgb[2], __uint_as_float(bx), __uint_as_float(by));
+        clamped[idx] = (uint8_t)clamp_bits;
+
+        radius_out = (int)radius;
+        tiles_out = (uint32_t)((ry1 - ry0) * (rx1 - rx0));
+        key_out = __float_as_uint(p_view.z);
+    } while (false);
+
+    radii[idx] = radius_out;
+    tiles_touched[idx] = tiles_out;
+    depth_key[idx] = key_out;
+    idx_in[idx] = (uint32_t)idx;
+}
+
+void launch_preprocess_fwd(const PreprocessFwdArgs &a, cudaStream_t stream)
+{
+    if (a.P == 0) return;
+    preprocess_fwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(
+        a.P, a.D, a.M, a.means3D, reinterpret_cast<const float2 *>(a.scales), a.scale_modifier,
+        reinterpret_cast<const float4 *>(a.rotations), a.opacities, a.shs, a.transMat_precomp, a.colors_precomp,
+        a.viewmatrix, a.projmatrix, a.cam_pos, a.W, a.H, a.gx, a.gy, a.radii, a.rec, a.tiles_touched, a.depth_key,
+        a.idx_in, a.clamped, a.prefiltered);
+}
+
+// =============================================================================================
+// K0: markVisible (rasterizer_impl.cu:54-66)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+mark_visible_kernel(const int P, const float *__restrict__ means3D, const float *__restrict__ viewmatrix,
+                    unsigned char *__restrict__ present)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float3 p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    const float3 pv = xform_point(p, viewmatrix);
+    present[idx] = pv.z > 0.2f ? 1 : 0;
+}
+
+void launch_mark_visible(int P, const float *means3D, const float *viewmatrix, unsigned char *present,
+                         cudaStream_t stream)
+{
+    if (P == 0) return;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+}
+
+// =============================================================================================
+// K8: backward preprocess.  One thread per Gaussian; consumes the gradient accumulator record
+// written by the backward render kernel and writes EVERY output element (zeros for culled
+// Gaussians), so callers never pre-zero 304 B/Gaussian as the reference binding does.
+// =============================================================================================
+__device__ __forceinline__ float4 quat_vjp(const float4 q, const float vR[3][3])
+{  // auxiliary.h:238-282, gradient w.r.t. the normalised quaternion taken as free (quirk 1)
+    const float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    const float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
+    float4 v;
+    v.x = 2.f * (x * (vR[1][2] - vR[2][1]) + y * (vR[2][0] - vR[0][2]) + z * (vR[0][1] - vR[1][0]));
+    v.y = 2.f * (-2.f * x * (vR[1][1] + vR[2][2]) + y * (vR[0][1] + vR[1][0]) + z * (vR[0][2] + vR[2][0]) +
+                 w * (vR[1][2] - vR[2][1]));
+    v.z = 2.f * (x * (vR[0][1] + vR[1][0]) - 2.f * y * (vR[0][0] + vR[2][2]) + z * (vR[1][2] + vR[2][1]) +
+                 w * (vR[2][0] - vR[0][2]));
+    v.w = 2.f * (x * (vR[0][2] + vR[2][0]) + y * (vR[1][2] + vR[2][1]) - 2.f * z * (vR[0][0] + vR[1][1]) +
+                 w * (vR[0][1] - vR[1][0]));
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_bwd_kernel(const int P, const int D, const int M, const float *__restrict__ means3D,
+                      const int *__restrict__ radii, const float *__restrict__ shs,
+                      const uint8_t *__restrict__ clamped, const float2 *__restrict__ scales,
+                      const float4 *__restrict__ rotations, const float *__restrict__ transMat_precomp,
+                      const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
+                      const float focal_x, const float focal_y, const float tan_fovx, const float tan_fovy,
+                      const float *__restrict__ cam_pos, const float *__restrict__ rec,
+                      const float *__restrict__ gacc, float *__restrict__ dL_dmean2D, float *__restrict__ dL_dnormal,
+                      float *__restrict__ dL_dopacity, float *__restrict__ dL_dcolor, float *__restrict__ dL_dmean3D,
+                      float *__restrict__ dL_dtransMat, float *__restrict__ dL_dsh, float2 *__restrict__ dL_dscale,
+                      float4 *__restrict__ dL_drot)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+
+    float o_m2x = 0.f, o_m2y = 0.f, o_op = 0.f;
+    float o_col[3] = {0.f, 0.f, 0.f}, o_nrm[3] = {0.f, 0.f, 0.f}, o_m3[3] = {0.f, 0.f, 0.f};
+    float o_T[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float2 o_sc = make_float2(0.f, 0.f);
+    float4 o_rot = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool have_sh = (shs != nullptr) && M > 0;
+    const bool visible = radii[idx] > 0;
+    float dRGB[3] = {0.f, 0.f, 0.f};
+    float dirx = 0.f, diry = 0.f, dirz = 0.f;
+
+    if (visible) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(gacc + (size_t)idx * GACC_FLOATS);
+        const float4 a0 = g4[0], a1 = g4[1], a2 = g4[2], a3 = g4[3], a4 = g4[4];
+        float dT[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};
+        float dm2x = a2.y, dm2y = a2.z;
+        o_op = a2.w;
+        o_col[0] = a3.x; o_col[1] = a3.y; o_col[2] = a3.z;
+        o_nrm[0] = a3.w; o_nrm[1] = a4.x; o_nrm[2] = a4.y;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) o_T[3 * j + r] = dT[j][r];
+
+        const int Wb = int(focal_x * tan_fovx * 2);  // backward.cu:613-614 (fp32 round trip, quirk 3)
+        const int Hb = int(focal_y * tan_fovy * 2);
+        const bool precomp = (scales == nullptr);     // backward.cu:615
+        const float3 p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+
+        float Tm[3][3], Pm[3][4], R[3][3];
+        float3 normal = make_float3(0.f, 0.f, 0.f);
+        float2 sc = make_float2(0.f, 0.f);
+        float4 q = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (precomp) {
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) Tm[j][r] = transMat_precomp[9 * idx + 3 * j + r];
+        } else {
+            float L[3][3];
+            sc = scales[idx];
+            q = rotations[idx];
+            quat_columns(q, R);
+            scaled_frame(R, 1.0f * sc.x, 1.0f * sc.y, L);  // scale_modifier ignored (quirk 2)
+            const float A[4][3] = {{L[0][0], L[1][0], p_orig.x}, {L[0][1], L[1][1], p_orig.y},
+                                   {L[0][2], L[1][2], p_orig.z}, {0.f, 0.f, 1.f}};
+            const float N[3][4] = {{float(Wb) / 2.0f, 0.f, 0.f, float(Wb - 1) / 2.0f},
+                                   {0.f, float(Hb) / 2.0f, 0.f, float(Hb - 1) / 2.0f},
+                                   {0.f, 0.f, 0.f, 1.f}};
+            // P = world2ndc * ndc2pix, world2ndc[c][r] = projmatrix[c + 4r]
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    Pm[j][r] = projmatrix[0 + 4 * r] * N[j][0] + projmatrix[1 + 4 * r] * N[j][1] +
+                               projmatrix[2 + 4 * r] * N[j][2] + projmatrix[3 + 4 * r] * N[j][3];
+            // T = transpose(M) * P
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    Tm[j][r] = A[0][r] * Pm[j][0] + A[1][r] * Pm[j][1] + A[2][r] * Pm[j][2] + A[3][r] * Pm[j][3];
+            normal = xform_vec(make_float3(L[2][0], L[2][1], L[2][2]), viewmatrix);
+        }
+
+        bool early = false;
+        if (dm2x != 0 || dm2y != 0) {  // backward.cu:519-549: fold dL/dmean2D through the centre formula
+            const float tv[3] = {9.0f, 9.0f, -1.0f};
+            const float d = dot3(tv[0], tv[1], tv[2], Tm[2][0] * Tm[2][0], Tm[2][1] * Tm[2][1], Tm[2][2] * Tm[2][2]);
+            const float invd = 1.0f / d;
+            float f[3], dT3[3], df[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) f[r] = tv[r] * invd;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                dT[0][r] += dm2x * f[r] * Tm[2][r];
+                dT[1][r] += dm2y * f[r] * Tm[2][r];
+                dT3[r] = dm2x * f[r] * Tm[0][r] + dm2y * f[r] * Tm[1][r];
+                df[r] = dm2x * Tm[0][r] * Tm[2][r] + dm2y * Tm[1][r] * Tm[2][r];
+            }
+            const float dL_dd = dot3(df[0], df[1], df[2], f[0], f[1], f[2]) * (-1.0 / d);
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const float dd_dT3 = tv[r] * Tm[2][r] * 2.0f;
+                dT3[r] += dL_dd * dd_dT3;
+                dT[2][r] += dT3[r];
+            }
+            if (precomp) {
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int r = 0; r < 3; r++) o_T[3 * j + r] = dT[j][r];
+                early = true;
+            }
+        }
+        if (!precomp && !early) {
+            // dL_dM = P * transpose(dL_dT)
+            float dM[3][4];
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) dM[j][r] = Pm[0][r] * dT[0][j] + Pm[1][r] * dT[1][j] + Pm[2][r] * dT[2][j];
+            float3 dtn = xform_vec_transposed(make_float3(o_nrm[0], o_nrm[1], o_nrm[2]), viewmatrix);
+            const float3 p_view = xform_point(p_orig, viewmatrix);
+            const float cosv = -(p_view.x * normal.x + p_view.y * normal.y + p_view.z * normal.z);
+            const float mult = cosv > 0 ? 1.f : -1.f;
+            dtn = make_float3(mult * dtn.x, mult * dtn.y, mult * dtn.z);
+            const float dRS[3][3] = {{dM[0][0], dM[0][1], dM[0][2]}, {dM[1][0], dM[1][1], dM[1][2]}, {dtn.x, dtn.y, dtn.z}};
+            float dR[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                dR[0][r] = dRS[0][r] * sc.x;
+                dR[1][r] = dRS[1][r] * sc.y;
+                dR[2][r] = dRS[2][r];
+            }
+            o_rot = quat_vjp(q, dR);
+            o_sc.x = dot3(dRS[0][0], dRS[0][1], dRS[0][2], R[0][0], R[0][1], R[0][2]);
+            o_sc.y = dot3(dRS[1][0], dRS[1][1], dRS[1][2], R[1][0], R[1][1], R[1][2]);
+            o_m3[0] = dM[2][0]; o_m3[1] = dM[2][1]; o_m3[2] = dM[2][2];
+        }
+
+        if (have_sh) {
+            const float3 cam = make_float3(cam_pos[0], cam_pos[1], cam_pos[2]);
+            dirx = p_orig.x - cam.x; diry = p_orig.y - cam.y; dirz = p_orig.z - cam.z;
+            const uint32_t cb = clamped[idx];
+#pragma unroll
+            for (int c = 0; c < 3; c++) dRGB[c] = o_col[c] * (((cb >> c) & 1u) ? 0.f : 1.f);
+        }
+
+        // densification proxy (backward.cu:631-635, quirk 4): uses forward's Tw.z and the
+        // (possibly folded, precomp path only) dL_dtransMat
+        const float depth = rec[(size_t)idx * REC_FLOATS + 8];
+        o_m2x = o_T[2] * depth * 0.5 * float(Wb);
+        o_m2y = o_T[5] * depth * 0.5 * float(Hb);
+    }
+
+    // ---- SH VJP (backward.cu:20-139); also writes the zero rows of culled Gaussians ----
+    if (have_sh) {
+        float *dsh = dL_dsh + (size_t)idx * M * 3;
+        if (!visible) {
+            for (int i = 0; i < 3 * M; i++) dsh[i] = 0.f;
+        } else {
+            const float len = sqrtf(dot3(dirx, diry, dirz, dirx, diry, dirz));
+            const float x = dirx / len, y = diry / len, z = dirz / len;
+            const float *sh = shs + (size_t)idx * M * 3;
+            float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
+#define SH(k, c) __ldg(sh + 3 * (k) + (c))
+#define DSH(k, v)                                             \
+    {                                                         \
+        const float vv = (v);                                 \
+        dsh[3 * (k)] = vv * dRGB[0];                          \
+        dsh[3 * (k) + 1] = vv * dRGB[1];                      \
+        dsh[3 * (k) + 2] = vv * dRGB[2];                      \
+    }
+            DSH(0, kSH_C0);
+            if (D > 0) {
+                DSH(1, -kSH_C1 * y);
+                DSH(2, kSH_C1 * z);
+                DSH(3, -kSH_C1 * x);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    dRGBdx[c] = -kSH_C1 * SH(3, c);
+                    dRGBdy[c] = -kSH_C1 * SH(1, c);
+                    dRGBdz[c] = kSH_C1 * SH(2, c);
+                }
+                if (D > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    DSH(4, kSH_C2[0] * xy);
+                    DSH(5, kSH_C2[1] * yz);
+                    DSH(6, kSH_C2[2] * (2.f * zz - xx - yy));
+                    DSH(7, kSH_C2[3] * xz);
+                    DSH(8, kSH_C2[4] * (xx - yy));
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        dRGBdx[c] += kSH_C2[0] * y * SH(4, c) + kSH_C2[2] * 2.f * -x * SH(6, c) + kSH_C2[3] * z * SH(7, c) +
+                                     kSH_C2[4] * 2.f * x * SH(8, c);
+                        dRGBdy[c] += kSH_C2[0] * x * SH(4, c) + kSH_C2[1] * z * SH(5, c) + kSH_C2[2] * 2.f * -y * SH(6, c) +
+                                     kSH_C2[4] * 2.f * -y * SH(8, c);
+                        dRGBdz[c] += kSH_C2[1] * y * SH(5, c) + kSH_C2[2] * 2.f * 2.f * z * SH(6, c) + kSH_C2[3] * x * SH(7, c);
+                    }
+                    if (D > 2) {
+                        DSH(9, kSH_C3[0] * y * (3.f * xx - yy));
+                        DSH(10, kSH_C3[1] * xy * z);
+                        DSH(11, kSH_C3[2] * y * (4.f * zz - xx - yy));
+                        DSH(12, kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
+                        DSH(13, kSH_C3[4] * x * (4.f * zz - xx - yy));
+                        DSH(14, kSH_C3[5] * z * (xx - yy));
+                        DSH(15, kSH_C3[6] * x * (xx - 3.f * yy));
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            dRGBdx[c] += (kSH_C3[0] * SH(9, c) * 3.f * 2.f * xy + kSH_C3[1] * SH(10, c) * yz +
+                                          kSH_C3[2] * SH(11, c) * -2.f * xy + kSH_C3[3] * SH(12, c) * -3.f * 2.f * xz +
+                                          kSH_C3[4] * SH(13, c) * (-3.f * xx + 4.f * zz - yy) +
+                                          kSH_C3[5] * SH(14, c) * 2.f * xz + kSH_C3[6] * SH(15, c) * 3.f * (xx - yy));
+                            dRGBdy[c] += (kSH_C3[0] * SH(9, c) * 3.f * (xx - yy) + kSH_C3[1] * SH(10, c) * xz +
+                                          kSH_C3[2] * SH(11, c) * (-3.f * yy + 4.f * zz - xx) +
+                                          kSH_C3[3] * SH(12, c) * -3.f * 2.f * yz + kSH_C3[4] * SH(13, c) * -2.f * xy +
+                                          kSH_C3[5] * SH(14, c) * -2.f * yz + kSH_C3[6] * SH(15, c) * -3.f * 2.f * xy);
+                            dRGBdz[c] += (kSH_C3[1] * SH(10, c) * xy + kSH_C3[2] * SH(11, c) * 4.f * 2.f * yz +
+                                          kSH_C3[3] * SH(12, c) * 3.f * (2.f * zz - xx - yy) +
+                                          kSH_C3[4] * SH(13, c) * 4.f * 2.f * xz + kSH_C3[5] * SH(14, c) * (xx - yy));
+                        }
+                    }
+                }
+            }
+            // coefficients above the active degree receive exact zeros
+            for (int k = (D + 1) * (D + 1); k < M; k++) DSH(k, 0.f);
+#undef SH
+#undef DSH
+            const float ddx = dot3(dRGBdx[0], dRGBdx[1], dRGBdx[2], dRGB[0], dRGB[1], dRGB[2]);
+            const float ddy = dot3(dRGBdy[0], dRGBdy[1], dRGBdy[2], dRGB[0], dRGB[1], dRGB[2]);
+            const float ddz = dot3(dRGBdz[0], dRGBdz[1], dRGBdz[2], dRGB[0], dRGB[1], dRGB[2]);
+            // normalisation Jacobian (auxiliary.h:128-138); "+=" on top of the geometric term (quirk 6)
+            const float sum2 = dirx * dirx + diry * diry + dirz * dirz;
+            const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
+            o_m3[0] += ((+sum2 - dirx * dirx) * ddx - diry * dirx * ddy - dirz * dirx * ddz) * invsum32;
+            o_m3[1] += (-dirx * diry * ddx + (sum2 - diry * diry) * ddy - dirz * diry * ddz) * invsum32;
+            o_m3[2] += (-dirx * dirz * ddx - diry * dirz * ddy + (sum2 - dirz * dirz) * ddz) * invsum32;
+        }
+    }
+
+    dL_dmean2D[3 * idx] = o_m2x;
+    dL_dmean2D[3 * idx + 1] = o_m2y;
+    dL_dmean2D[3 * idx + 2] = 0.f;
+    dL_dopacity[idx] = o_op;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        dL_dcolor[3 * idx + c] = o_col[c];
+        dL_dmean3D[3 * idx + c] = o_m3[c];
+        if (dL_dnormal) dL_dnormal[3 * idx + c] = o_nrm[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) dL_dtransMat[9 * idx + i] = o_T[i];
+    dL_dscale[idx] = o_sc;
+    dL_drot[idx] = o_rot;
+}
+
+void launch_preprocess_bwd(const PreprocessBwdArgs &a, cudaStream_t stream)
+{
+    if (a.P == 0) return;
+    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(
+        a.P, a.D, a.M, a.means3D, a.radii, a.shs, a.clamped, reinterpret_cast<const float2 *>(a.scales),
+        reinterpret_cast<const float4 *>(a.rotations), a.transMat_precomp, a.viewmatrix, a.projmatrix, a.focal_x,
+        a.focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, a.rec, a.gacc, a.dL_dmean2D, a.dL_dnormal, a.dL_dopacity,
+        a.dL_dcolor, a.dL_dmean3D, a.dL_dtransMat, a.dL_dsh, reinterpret_cast<float2 *>(a.dL_dscale),
+        reinterpret_cast<float4 *>(a.dL_drot));
+}
+
+}  // namespace surfel

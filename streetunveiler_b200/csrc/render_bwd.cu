@@ -1,0 +1,308 @@
+// render_bwd.cu -- K7: back-to-front gradient pass of the tile blend.
+//
+// Behavioural specification: RAST/cuda_rasterizer/backward.cu:143-446 (renderCUDA); the per-pixel
+// recurrences are restated in SURVEY.md Appendix A ("Backward, per pixel") and reproduced with
+// the reference's conventions (its quirks 5, 8: clamp ignored, tie goes to the 3-D branch,
+// mixed-sign median comparison).
+//
+// What is different from the reference kernel (which issues up to 16 scalar float atomicAdds per
+// contributing pixel-instance, backward.cu:339-443):
+//   * the same packed 80-B records / TMA bulk gather / 8x4-pixel warp blocks / per-warp batch
+//     compaction as the forward kernel, plus a per-tile bound (max last contributor, saved by the
+//     forward) so the list tail nobody blended is never even loaded;
+//   * the 18 per-instance gradient values are summed over the warp's 32 pixels with a
+//     multi-value butterfly (20 shuffles for all 18 values, not 18 x 5), leaving one value per
+//     lane, and flushed with ONE reduction instruction per (warp, instance) into an 80-B
+//     per-Gaussian accumulator record that the backward-preprocess kernel consumes.
+#include "async_copy.cuh"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace surfel {
+
+constexpr int BWD_BATCH = 256;
+constexpr int NV = 18;  // gradient values per instance
+
+// Multi-value warp reduction: N values per lane in, one fully reduced value per lane out.
+// Each xor step halves the number of live values; lanes with the step's bit set keep the upper half.
+template <int N, int BIT>
+struct Butterfly {
+    static constexpr int H = (N + 1) / 2;
+    __device__ __forceinline__ static void run(float (&v)[NV], const int lane)
+    {
+        const bool hi = (lane >> BIT) & 1;
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            const float upper = (i + H < N) ? v[i + H] : 0.f;
+            const float send = hi ? v[i] : upper;
+            const float keep = hi ? upper : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << BIT);
+        }
+        if constexpr (BIT > 0) Butterfly<H, BIT - 1>::run(v, lane);
+    }
+    // which of the original N values ends up in this lane's v[0] (-1: padding)
+    __device__ __forceinline__ static int slot(const int lane, const int base, const int count)
+    {
+        // count = number of real values in [0, N) at this level for this lane's branch
+        const bool hi = (lane >> BIT) & 1;
+        const int nb = hi ? base + H : base;
+        const int nc = hi ? count - H : (count < H ? count : H);
+        if (nc <= 0) return -1;
+        if constexpr (BIT > 0) return Butterfly<H, BIT - 1>::slot(lane, nb, nc);
+        return nb;
+    }
+};
+
+template <bool CULL>
+__global__ void __launch_bounds__(256)
+render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restrict__ ranges,
+                  const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
+                  const float *__restrict__ bg, const float *__restrict__ final_Ts,
+                  const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tile_max_contrib,
+                  const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dothers,
+                  float *__restrict__ gacc)
+{
+    __shared__ __align__(128) float s_rec[2][BWD_BATCH * REC_FLOATS];
+    __shared__ uint32_t s_id[2][BWD_BATCH];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    const int bx0 = tile_x * TILE_X + (warp & 1) * 8, by0 = tile_y * TILE_Y + (warp >> 1) * 4;
+    const uint32_t pix_x = bx0 + (lane & 7), pix_y = by0 + (lane >> 3);
+    const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+    const float2 pixf = make_float2((float)pix_x, (float)pix_y);
+    const size_t HW = (size_t)W * H;
+    const size_t pix_id = (size_t)W * pix_y + pix_x;
+
+    const uint2 range = ranges[tile];
+    // only list positions [0, total) can have been blended by some pixel of this tile
+    const int total = min((int)(range.y - range.x), (int)tile_max_contrib[tile]);
+    const int nbatch = (total + BWD_BATCH - 1) / BWD_BATCH;
+    if (nbatch == 0) return;
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // batch b, slot t  <->  list position  total - 1 - (b*BATCH + t)   (back to front)
+    auto issue = [&](int b) {
+        const int n = min(BWD_BATCH, total - b * BWD_BATCH);
+        const int buf = b & 1;
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar[buf], (uint32_t)n * REC_BYTES);
+        if (tid < n) {
+            const uint32_t id = point_list[range.x + (total - 1 - (b * BWD_BATCH + tid))];
+            s_id[buf][tid] = id;
+            bulk_g2s(&s_rec[buf][tid * REC_FLOATS], rec + (size_t)id * REC_FLOATS, REC_BYTES, &s_bar[buf]);
+        }
+    };
+
+    const float T_final = inside ? final_Ts[pix_id] : 0;
+    float T = T_final;
+    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0;
+    const int median_contributor = inside ? (int)n_contrib[pix_id + HW] : 0;
+    const uint32_t median_match = (uint32_t)(median_contributor - 1);  // backward.cu:347, unsigned compare
+
+    float accum_rec[3] = {0.f, 0.f, 0.f}, dL_dpixel[3] = {0.f, 0.f, 0.f};
+    float dL_dreg = 0.f, dL_ddepth = 0.f, dL_daccum = 0.f, dL_dmedian_depth = 0.f;
+    float dL_dnormal2D[3] = {0.f, 0.f, 0.f};
+    if (inside) {
+        dL_ddepth = dL_dothers[pix_id];
+        dL_daccum = dL_dothers[HW + pix_id];
+        dL_dnormal2D[0] = dL_dothers[2 * HW + pix_id];
+        dL_dnormal2D[1] = dL_dothers[3 * HW + pix_id];
+        dL_dnormal2D[2] = dL_dothers[4 * HW + pix_id];
+        dL_dmedian_depth = dL_dothers[5 * HW + pix_id];
+        dL_dreg = dL_dothers[6 * HW + pix_id];
+        dL_dpixel[0] = dL_dpixels[pix_id];
+        dL_dpixel[1] = dL_dpixels[HW + pix_id];
+        dL_dpixel[2] = dL_dpixels[2 * HW + pix_id];
+    }
+    float last_depth = 0.f, accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
+    float last_normal[3] = {0.f, 0.f, 0.f}, accum_normal_rec[3] = {0.f, 0.f, 0.f};
+    const float final_D = inside ? final_Ts[pix_id + HW] : 0;
+    const float final_D2 = inside ? final_Ts[pix_id + 2 * HW] : 0;
+    const float final_A = 1 - T_final;
+    float last_alpha = 0.f, last_color[3] = {0.f, 0.f, 0.f};
+    float bg_dot_dpixel = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) bg_dot_dpixel += bg[i] * dL_dpixel[i];
+
+    // highest list position any pixel of this warp blended, +1
+    uint32_t warp_last = last_contributor;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+
+    const int my_slot = Butterfly<NV, 4>::slot(lane, 0, NV);
+
+    issue(0);
+    __syncthreads();  // s_id[0] visible (later batches are published by the end-of-iteration barrier)
+    uint32_t phase[2] = {0u, 0u};
+
+    for (int b = 0; b < nbatch; b++) {
+        const int buf = b & 1;
+        if (b + 1 < nbatch) issue(b + 1);
+        mbar_wait(&s_bar[buf], phase[buf]);
+        phase[buf] ^= 1u;
+
+        const int n = min(BWD_BATCH, total - b * BWD_BATCH);
+        const float *sb = s_rec[buf];
+        for (int c = 0; c < n; c += 32) {
+            // chunk slot (c + lane) holds list position pos_first - lane (descending)
+            const int pos_first = total - 1 - (b * BWD_BATCH + c);
+            const int pos_min = pos_first - (min(32, n - c) - 1);
+            if ((uint32_t)pos_min >= warp_last) continue;  // entirely behind everything this warp blended
+            uint32_t mask;
+            {
+                const int j = c + lane;
+                bool hit = false;
+                if (j < n) {
+                    const int pos = pos_first - lane;
+                    hit = (uint32_t)pos < warp_last;
+                    if (CULL && hit) {
+                        const uint2 bb = *reinterpret_cast<const uint2 *>(sb + j * REC_FLOATS + 18);
+                        const int x0 = bb.x & 0xffff, x1 = bb.x >> 16, y0 = bb.y & 0xffff, y1 = bb.y >> 16;
+                        hit = (x0 <= bx0 + 7) && (x1 >= bx0) && (y0 <= by0 + 3) && (y1 >= by0);
+                    }
+                }
+                mask = __ballot_sync(0xffffffffu, hit);
+            }
+            while (mask) {
+                const int sl = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int jj = c + sl;
+                const uint32_t contributor = (uint32_t)(pos_first - sl);  // reference's `contributor` after --
+
+                float v[NV];
+#pragma unroll
+                for (int i = 0; i < NV; i++) v[i] = 0.f;
+                bool valid = false;
+
+                if (contributor < last_contributor) {
+                    const float4 *r4 = reinterpret_cast<const float4 *>(sb + jj * REC_FLOATS);
+                    const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
+                    const float3 Tu = make_float3(q0.x, q0.y, q0.z);
+                    const float3 Tv = make_float3(q0.w, q1.x, q1.y);
+                    const float3 Tw = make_float3(q1.z, q1.w, q2.x);
+                    const float3 k = make_float3(pixf.x * Tw.x - Tu.x, pixf.x * Tw.y - Tu.y, pixf.x * Tw.z - Tu.z);
+                    const float3 l = make_float3(pixf.y * Tw.x - Tv.x, pixf.y * Tw.y - Tv.y, pixf.y * Tw.z - Tv.z);
+                    const float3 p = make_float3(k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x);
+                    if (p.z != 0.0f) {
+                        const float2 s = make_float2(p.x / p.z, p.y / p.z);
+                        const float rho3d = (s.x * s.x + s.y * s.y);
+                        const float2 d = make_float2(q2.y - pixf.x, q2.z - pixf.y);
+                        const float rho2d = FILTER_INV_SQUARE * (d.x * d.x + d.y * d.y);
+                        const float rho = fminf(rho3d, rho2d);
+                        const float c_d = (s.x * Tw.x + s.y * Tw.y) + Tw.z;
+                        const float power = -0.5f * rho;
+                        if (!(c_d < NEAR_N) && !(power > 0.0f)) {
+                            const float G = expf(power);
+                            const float opa = q2.w;
+                            const float alpha = fminf(0.99f, opa * G);
+                            if (!(alpha < ALPHA_MIN)) {
+                                valid = true;
+                                const float4 q3 = r4[3], q4 = r4[4];
+                                const float normal[3] = {q3.x, q3.y, q3.z};
+                                const float col[3] = {q3.w, q4.x, q4.y};
+
+                                T = T / (1.f - alpha);
+                                const float w = alpha * T;
+                                float dL_dalpha = 0.0f;
+#pragma unroll
+                                for (int ch = 0; ch < 3; ch++) {
+                                    const float cc = col[ch];
+                                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                                    last_color[ch] = cc;
+                                    dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
+                                    v[12 + ch] = w * dL_dpixel[ch];
+                                }
+                                float dL_dz = 0.0f;
+                                float dL_dweight = 0;
+                                const float m_d = FAR_N / (FAR_N - NEAR_N) * (1 - NEAR_N / c_d);
+                                const float dmd_dd = (FAR_N * NEAR_N) / ((FAR_N - NEAR_N) * c_d * c_d);
+                                if (contributor == median_match) dL_dz += dL_dmedian_depth;
+                                dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
+                                dL_dalpha += dL_dweight - last_dL_dT;
+                                last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
+                                const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+                                dL_dz += dL_dmd * dmd_dd;
+
+                                accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
+                                last_depth = c_d;
+                                dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+                                accum_alpha_rec = last_alpha * 1.0 + (1.f - last_alpha) * accum_alpha_rec;
+                                dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
+#pragma unroll
+                                for (int ch = 0; ch < 3; ch++) {
+                                    accum_normal_rec[ch] =
+                                        last_alpha * last_normal[ch] + (1.f - last_alpha) * accum_normal_rec[ch];
+                                    last_normal[ch] = normal[ch];
+                                    dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
+                                    v[15 + ch] = alpha * T * dL_dnormal2D[ch];
+                                }
+                                dL_dalpha *= T;
+                                last_alpha = alpha;
+                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                                const float dL_dG = opa * dL_dalpha;
+                                dL_dz += alpha * T * dL_ddepth;
+
+                                if (rho3d <= rho2d) {
+                                    const float2 dL_ds = make_float2(dL_dG * -G * s.x + dL_dz * Tw.x,
+                                                                     dL_dG * -G * s.y + dL_dz * Tw.y);
+                                    const float dsx_pz = dL_ds.x / p.z;
+                                    const float dsy_pz = dL_ds.y / p.z;
+                                    const float3 dL_dp = make_float3(dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y));
+                                    const float3 dL_dk = make_float3(l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z,
+                                                                     l.x * dL_dp.y - l.y * dL_dp.x);
+                                    const float3 dL_dl = make_float3(dL_dp.y * k.z - dL_dp.z * k.y, dL_dp.z * k.x - dL_dp.x * k.z,
+                                                                     dL_dp.x * k.y - dL_dp.y * k.x);
+                                    v[0] = -dL_dk.x; v[1] = -dL_dk.y; v[2] = -dL_dk.z;
+                                    v[3] = -dL_dl.x; v[4] = -dL_dl.y; v[5] = -dL_dl.z;
+                                    v[6] = pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x;
+                                    v[7] = pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y;
+                                    v[8] = pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz * 1.0f;
+                                } else {
+                                    const float dG_ddelx = -G * FILTER_INV_SQUARE * d.x;
+                                    const float dG_ddely = -G * FILTER_INV_SQUARE * d.y;
+                                    v[9] = dL_dG * dG_ddelx;
+                                    v[10] = dL_dG * dG_ddely;
+                                    v[6] = s.x * dL_dz;
+                                    v[7] = s.y * dL_dz;
+                                    v[8] = dL_dz;
+                                }
+                                v[11] = G * dL_dalpha;
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, valid)) {
+                    Butterfly<NV, 4>::run(v, lane);
+                    if (my_slot >= 0) atomicAdd(gacc + (size_t)s_id[buf][jj] * GACC_FLOATS + my_slot, v[0]);
+                }
+            }
+        }
+        __syncthreads();  // all warps finished with this buffer before it is refilled
+    }
+}
+
+void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
+{
+    const int tiles = a.gx * a.gy;
+    if (tiles == 0) return;
+    if (a.subtile_cull)
+        render_bwd_kernel<true><<<tiles, 256, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
+                                                           a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
+                                                           a.dL_dothers, a.gacc);
+    else
+        render_bwd_kernel<false><<<tiles, 256, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
+                                                            a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
+                                                            a.dL_dothers, a.gacc);
+}
+
+}  // namespace surfel
