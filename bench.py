@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd throughput of the surfel rasterizer on synthetic street scenes.
+
+Metric (BASELINE.json): M Gaussians/s fwd+bwd @1920x1280 = P / (t_fwd + t_bwd) / 1e6.
+A "step" is one forward + one backward of the rasterizer operator over one synthetic scene.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu]
+
+  * N = 1 (default): BASELINE config 3 -- STREET(P=2,000,000, seed 1), CAM-A 1920x1280, SH degree 3,
+    colour + alpha upstream gradients.
+  * N > 1 (torchrun, one rank per GPU): weak scaling -- every rank owns a depth slab of 2,000,000
+    surfels of one STREET(2,000,000*N) scene and the ranks composite their slabs into one image
+    (streetunveiler_b200/sharded.py).
+  * --impl reference: the UNMODIFIED reference CUDA extension rebuilt for sm_100a (oracle/_ref), same
+    inputs and timing protocol, on the same GPU; falls back to the CPU oracle port when that build
+    is absent.  --impl reference-cpu forces the CPU oracle port (host cores).
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks; inputs (>460 MB) are larger than the 126 MB L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from streetunveiler_b200 import synthetic as syn  # noqa: E402
+
+METRIC = "M Gaussians/s fwd+bwd @1920x1280"
+UNIT = "MGaussians/s"
+P_PER_GPU = 2_000_000
+HAND_WRITTEN_LAUNCHES_PER_STEP = 6  # preprocess_fwd, emit_instances, tile_ranges, render_fwd, render_bwd, preprocess_bwd
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            out["samples"] = len(sm)
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                seen = set()
+                for r in rows:
+                    for n, v in zip(names, r[5:9]):
+                        if v.strip().lower().startswith("active"):
+                            seen.add(n)
+                out["reasons"] = sorted(seen)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def alg_bytes_step(P, R, HW, K=16):
+    """ALG_BYTES = (IN + 4 + IN + OUT) P + 36 R + 80 HW with IN = 40 + 12K, OUT = 52 + 12K."""
+    IN = 12 + 8 + 16 + 4 + 12 * K
+    OUT = 12 + 12 + 4 + 8 + 16 + 12 * K
+    return (IN + 4 + IN + OUT) * P + 36 * R + 80 * HW
+
+
+def alg_bytes_stage(stage, P, P_vis, R, HW, K=16):
+    """Compulsory (cache-perfect) bytes of each stage of OUR pipeline; stated in DESIGN.md section 5."""
+    IN = 12 + 8 + 16 + 4 + 12 * K
+    OUT = 12 + 12 + 4 + 8 + 16 + 12 * K
+    return {
+        "preprocess_fwd": P * (40 + 4 + 4 + 4 + 4) + P_vis * (12 * K + 80 + 1),   # params in; radii/tiles/key/iota out; SH in + record out
+        "depth_order": P * 8 * 2 * 4 + P * 12,                                    # 4 digit passes of 8 B pairs (r+w) + scan
+        "tile_binning": P * 12 + R * 8 + R * 16 * 2 + R * 4,                      # emit 8 B/inst, 2 digit passes r+w, ranges read
+        "render_fwd": R * 4 + P_vis * 80 + HW * 60,                               # ids + each record once + 15 planes out
+        "render_bwd": R * 4 + P_vis * (80 + 72) + HW * 60,                        # ids + records + grad record out + 15 planes in
+        "preprocess_bwd": P * 4 + P_vis * (IN + 80 + 72) + P * OUT,               # radii; params+record+grad record in; grads out
+    }[stage]
+
+
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    """One rank's share of the synthetic scene, resident on its GPU."""
+
+    def __init__(self, P_total, seed, world, rank, device):
+        self.cam = syn.cam_a()
+        scene = syn.street_scene(P_total, seed, 3)
+        if world > 1:
+            order = syn.depth_separable_order(scene["means3D"], self.cam)
+            lo, hi = rank * (P_total // world), (rank + 1) * (P_total // world)
+            sel = order[lo:hi]
+            scene = {k: (v[sel].contiguous() if isinstance(v, torch.Tensor) else v) for k, v in scene.items()}
+        self.host = scene
+        self.crc = syn.scene_crc(scene)
+        self.P = scene["means3D"].shape[0]
+        self.device = device
+        self.dev = {k: v.to(device) for k, v in scene.items() if isinstance(v, torch.Tensor)}
+        dc, da = syn.upstream_grads(self.cam.width, self.cam.height, "color_alpha")
+        self.grads_host = (dc, da)
+        self.grads = (dc.to(device), da.to(device))
+        self.bg = torch.zeros(3, device=device)
+
+
+def make_step(mod, wl: Workload, sharded=None):
+    import harness as hz
+    st = hz._settings(mod, wl.cam, torch.zeros(3), 3, 1.0, wl.device)
+    rast = mod.GaussianRasterizer(st)
+    leaves = {k: wl.dev[k].detach().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    state = {}
+
+    def step():
+        for t in list(leaves.values()) + [m2]:
+            t.grad = None
+        if sharded is None:
+            color, radii, allmap = rast(means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"],
+                                        shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+        else:
+            color, radii, allmap = sharded(leaves["means3D"], m2, leaves["opacities"], leaves["shs"], leaves["scales"],
+                                           leaves["rotations"], st)
+        torch.autograd.backward([color, allmap], [wl.grads[0], wl.grads[1]])
+        state["color"], state["allmap"], state["radii"] = color, allmap, radii
+        fn = color.grad_fn
+        state["R"] = getattr(fn, "num_rendered", None)
+        return state
+
+    return step, leaves, m2, state
+
+
+def timed_loop(fn, steps, warmup, world, device):
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+        torch.distributed.barrier()
+    return ms / steps
+
+
+def cpu_oracle_baseline(wl_host, cam, grads_host, threads=None):
+    """Oracle port timed on the host cores (whole workload, one step)."""
+    from oracle import oracle
+    if threads:
+        oracle.set_num_threads(threads)
+    t0 = time.time()
+    f = oracle.rasterize_forward(torch.zeros(3), wl_host["means3D"], None, wl_host["opacities"], wl_host["scales"],
+                                 wl_host["rotations"], 1.0, None, cam.viewmatrix, cam.projmatrix, cam.tanfovx,
+                                 cam.tanfovy, cam.height, cam.width, wl_host["shs"], 3, cam.campos)
+    oracle.rasterize_backward(f, grads_host[0], grads_host[1])
+    dt = time.time() - t0
+    return wl_host["means3D"].shape[0] / dt / 1e6, dt, oracle.num_threads()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    from streetunveiler_b200 import _lib
+    import harness as hz
+    mod = hz.ours_module()
+
+    P_total = P_PER_GPU * world
+    wl = Workload(P_total, 1 if world == 1 else 2, world, rank, device)
+    sharded = None
+    if world > 1:
+        from streetunveiler_b200.sharded import ShardedRasterizer
+        sharded = ShardedRasterizer(world, rank)
+    step, leaves, m2, state = make_step(mod, wl, sharded)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step = timed_loop(step, args.steps, args.warmup, world, device)
+    clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("BENCH_DEBUG"):
+        print("debug: R after timed loop", state["R"], file=sys.stderr)
+
+    # ---- e2e: host (pinned) buffers in, results out, every step ----
+    pin = {k: v.pin_memory() for k, v in wl.host.items() if isinstance(v, torch.Tensor)}
+    pin_g = [g.pin_memory() for g in wl.grads_host]
+    h2d = sum(v.numel() * v.element_size() for v in pin.values()) + sum(g.numel() * 4 for g in pin_g)
+    out_host = {}
+
+    def e2e_step():
+        for k in leaves:
+            leaves[k].data.copy_(pin[k], non_blocking=True)
+        wl.grads[0].copy_(pin_g[0], non_blocking=True)
+        wl.grads[1].copy_(pin_g[1], non_blocking=True)
+        s = step()
+        outs = {"color": s["color"], "allmap": s["allmap"], "radii": s["radii"], "g_means2D": m2.grad}
+        outs.update({"g_" + k: v.grad for k, v in leaves.items()})
+        for k, v in outs.items():
+            if k not in out_host:
+                out_host[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+            out_host[k].copy_(v.detach(), non_blocking=True)
+
+    ms_e2e = timed_loop(e2e_step, max(2, args.steps // 2), 1, world, device)
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+    if os.environ.get("BENCH_DEBUG"):
+        print("debug: R after e2e loop", state["R"], file=sys.stderr)
+
+    # ---- per-stage device time (roofline of the dominant kernel) ----
+    roof = None
+    stages = {}
+    if world == 1:
+        _lib.set_option("time_stages", 1)
+        for _ in range(max(3, args.steps // 2)):
+            step()
+        torch.cuda.synchronize(device)
+        stages = {k: (ms / max(n, 1)) for k, (ms, n) in _lib.stage_times().items()}
+        _lib.set_option("time_stages", 0)
+
+    R = int(state["R"] or 0)
+    P_vis = int((state["radii"] > 0).sum().item())
+    HW = wl.cam.width * wl.cam.height
+    peak, peak_src = measured_peaks()
+    if stages:
+        dom = max(stages, key=stages.get)
+        ab = alg_bytes_stage(dom, wl.P, P_vis, R, HW)
+        achieved = ab / (stages[dom] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(dom)
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": int(ab), "ms_per_launch": round(stages[dom], 4)}
+
+    if rank != 0:
+        return
+    value = P_total / (ms_step * 1e-3) / 1e6
+    step_bytes = alg_bytes_step(wl.P, R, HW)
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"STREET(P={P_total}, seed={1 if world == 1 else 2}) CAM-A 1920x1280 SH3, "
+                               f"grads colour+alpha; BASELINE configs[2]" + ("" if world == 1 else
+                               f"; depth-slab shards of {P_PER_GPU} surfels per GPU, composited over NCCL"),
+                   "P_total": P_total, "P_per_gpu": wl.P, "num_rendered": R, "visible": P_vis, "input_crc32": wl.crc,
+                   "l2": "inputs (464 MB/GPU) larger than the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3)},
+        "gpu_launches": HAND_WRITTEN_LAUNCHES_PER_STEP * args.steps,
+        "gpu_launches_note": "hand-written kernels per step: preprocess_fwd, emit_instances, tile_ranges, render_fwd, "
+                             "render_bwd, preprocess_bwd (+ cub radix-sort/scan launches and 2 memsets, not counted)",
+        "roofline": roof,
+        "step_roofline": {"alg_bytes": int(step_bytes), "achieved_gbs": round(step_bytes / (ms_step * 1e-3) / 1e9, 2),
+                          "frac_of_peak": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),
+                          "formula": "712 P + 36 R + 80 HW (SURVEY.md 8d)"},
+        "stage_ms": {k: round(v, 4) for k, v in stages.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, th = cpu_oracle_baseline(wl.host, wl.cam, wl.grads_host)
+        line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": th, "kind": "port",
+                                "sample": f"whole workload (P={wl.P}), 1 step fwd+bwd of the C oracle, {dt:.1f} s"}
+    print(json.dumps(line))
+
+
+def run_reference(args, force_cpu=False):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    import harness as hz
+    use_gpu_ref = (not force_cpu) and torch.cuda.is_available() and hz.reference_available()
+    cam = syn.cam_a()
+    if use_gpu_ref:
+        device = torch.device("cuda", local)
+        torch.cuda.set_device(device)
+        wl = Workload(P_PER_GPU, 1, 1, 0, device)
+        step, leaves, m2, state = make_step(hz.reference_module(), wl)
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms_step = timed_loop(step, args.steps, args.warmup, 1, device)
+        clocks = sampler.stop()
+        value = wl.P / (ms_step * 1e-3) / 1e6
+        kind, cores = "reference", 0
+        sample = ("UNMODIFIED reference CUDA extension (oracle/_ref, rebuilt for sm_100a) on the same GPU, whole "
+                  "workload; the reference has no CPU implementation of this path")
+        R = int(state["R"] or 0)
+        crc = wl.crc
+    else:
+        scene = syn.street_scene(P_PER_GPU, 1, 3)
+        crc = syn.scene_crc(scene)
+        grads = syn.upstream_grads(cam.width, cam.height, "color_alpha")
+        times = []
+        for _ in range(max(1, min(args.steps, 2))):
+            v, dt, cores = cpu_oracle_baseline(scene, cam, grads)
+            times.append(dt)
+        ms_step = float(np.mean(times)) * 1e3
+        value = P_PER_GPU / (ms_step * 1e-3) / 1e6
+        kind, clocks, R = "port", None, None
+        sample = "C oracle port of the reference algorithm on all host threads, whole workload"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "STREET(P=2000000, seed=1) CAM-A 1920x1280 SH3, grads colour+alpha; BASELINE configs[2]",
+                   "num_rendered": R, "input_crc32": crc},
+        "clocks": clocks,
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "ours":
+        run_ours(args)
+    else:
+        run_reference(args, force_cpu=(args.impl == "reference-cpu"))
+
+
+if __name__ == "__main__":
+    main()

@@ -147,8 +147,27 @@ SURFEL_API int surfel_debug_copy_binning(int width, int height, int64_t num_rend
                               const char *binning_buffer, const char *image_buffer,
                               uint32_t *ranges_out, uint32_t *point_list_out, void *stream);
 
-/* Tuning / debug knobs: "subtile_cull" (default 1). Returns 0 if the option exists. */
+/* Debug view of the geometry scratch: per-Gaussian tile counts [P], depth-ordered ids [P], inclusive
+ * offsets [P] (all uint32) and the packed 80-byte projected records [P,20] (fp32 words). Any output
+ * may be NULL. */
+SURFEL_API int surfel_debug_copy_geometry(int P, const char *geometry_buffer, uint32_t *tiles_touched_out,
+                                          uint32_t *idx_sorted_out, uint32_t *offsets_out, float *records_out,
+                                          void *stream);
+
+/* Tuning / debug knobs: "subtile_cull" (default 1), "time_stages" (default 0; setting it clears the
+ * stage clocks).  Returns 0 if the option exists. */
 SURFEL_API int surfel_set_option(const char *name, int value);
+
+/*
+ * Per-stage device timing for roofline measurement (bench.py).  With "time_stages" = 1 every
+ * stage is bracketed by CUDA events on the launching stream (and the call synchronises on them):
+ * stages 0..surfel_stage_count()-1 = preprocess_fwd, depth_order, tile_binning, render_fwd,
+ * render_bwd, preprocess_bwd.  surfel_stage_time returns the accumulated milliseconds and the
+ * number of timed launches since the option was last set.
+ */
+SURFEL_API int surfel_stage_count(void);
+SURFEL_API const char *surfel_stage_name(int stage);
+SURFEL_API int surfel_stage_time(int stage, double *total_ms, int *calls);
 
 #ifdef __cplusplus
 }

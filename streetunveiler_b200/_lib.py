@@ -31,7 +31,11 @@ SIGNATURES = {
                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "surfel_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_copy_binning": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_debug_copy_geometry": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_set_option": (_i, [C.c_char_p, _i]),
+    "surfel_stage_count": (_i, []),
+    "surfel_stage_name": (C.c_char_p, [_i]),
+    "surfel_stage_time": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i)]),
 }
 
 
@@ -77,3 +81,18 @@ def size(n: int, what: str) -> int:
         msg = lib().surfel_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed: {msg}")
     return int(n)
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().surfel_set_option(name.encode(), int(value)), f"surfel_set_option({name})")
+
+
+def stage_times() -> dict:
+    """{stage name: (total ms, timed launches)} accumulated since time_stages was last set."""
+    L = lib()
+    out = {}
+    for i in range(L.surfel_stage_count()):
+        ms, n = C.c_double(0), C.c_int(0)
+        check(L.surfel_stage_time(i, C.byref(ms), C.byref(n)), "surfel_stage_time")
+        out[L.surfel_stage_name(i).decode()] = (ms.value, n.value)
+    return out

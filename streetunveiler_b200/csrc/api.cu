@@ -18,6 +18,42 @@ namespace {
 thread_local std::string g_err;
 int g_subtile_cull = 1;
 
+// ---- optional per-stage device timing (bench.py roofline measurement) ----
+constexpr int N_STAGES = 6;
+const char *const kStageNames[N_STAGES] = {"preprocess_fwd", "depth_order", "tile_binning",
+                                           "render_fwd",     "render_bwd",  "preprocess_bwd"};
+int g_time_stages = 0;
+double g_stage_ms[N_STAGES] = {0, 0, 0, 0, 0, 0};
+int g_stage_calls[N_STAGES] = {0, 0, 0, 0, 0, 0};
+
+struct StageClock {  // brackets a stage with two events on the launching stream
+    cudaStream_t st;
+    int stage;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageClock(cudaStream_t s, int id) : st(s), stage(id)
+    {
+        if (!g_time_stages) return;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+    void stop()
+    {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) {
+            g_stage_ms[stage] += ms;
+            g_stage_calls[stage] += 1;
+        }
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        a = b = nullptr;
+    }
+    ~StageClock() { stop(); }
+};
+
 int fail(const char *where, const char *what)
 {
     g_err = std::string(where) + ": " + what;
@@ -108,12 +144,27 @@ extern "C" {
 
 int surfel_abi_version(void) { return SURFEL_ABI_VERSION; }
 
+int surfel_stage_count(void) { return N_STAGES; }
+const char *surfel_stage_name(int stage) { return (stage >= 0 && stage < N_STAGES) ? kStageNames[stage] : ""; }
+int surfel_stage_time(int stage, double *total_ms, int *calls)
+{
+    if (stage < 0 || stage >= N_STAGES || !total_ms || !calls) return fail("surfel_stage_time", "bad arguments");
+    *total_ms = g_stage_ms[stage];
+    *calls = g_stage_calls[stage];
+    return 0;
+}
+
 const char *surfel_last_error(void) { return g_err.c_str(); }
 
 int surfel_set_option(const char *name, int value)
 {
     if (name && std::strcmp(name, "subtile_cull") == 0) {
         g_subtile_cull = value;
+        return 0;
+    }
+    if (name && std::strcmp(name, "time_stages") == 0) {  // (re)arms and clears the stage clocks
+        g_time_stages = value;
+        for (int i = 0; i < N_STAGES; i++) { g_stage_ms[i] = 0; g_stage_calls[i] = 0; }
         return 0;
     }
     return fail("surfel_set_option", "unknown option");
@@ -187,11 +238,16 @@ int surfel_forward_prepare(int P, int D, int M, int width, int height, const flo
     a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
     a.radii = radii; a.rec = g.rec; a.tiles_touched = g.tiles_touched; a.depth_key = g.depth_key;
     a.idx_in = g.idx_in; a.clamped = g.clamped;
-    launch_preprocess_fwd(a, st);
+    {
+        StageClock clk(st, 0);
+        launch_preprocess_fwd(a, st);
+    }
     STAGE("preprocess");
 
+    StageClock clk_depth(st, 1);
     CK("depth order", run_depth_order(P, g.depth_key, g.depth_key_sorted, g.idx_in, g.idx_sorted, g.tiles_touched,
                                       g.offsets, g.num_rendered, g.cub_temp, g.cub_temp_bytes, st));
+    clk_depth.stop();
     STAGE("depth order");
 
     uint32_t r32 = 0;
@@ -221,9 +277,11 @@ int surfel_forward_render(int P, int width, int height, int64_t num_rendered, co
         const size_t cub = tile_sort_temp_bytes(num_rendered);
         bv = carve_bin(binning_buffer, num_rendered, cub);
     }
+    StageClock clk_bin(st, 2);
     CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, g.rec, radii, g.idx_sorted, g.offsets,
                                         bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted, bv.point_list, iv.ranges,
                                         bv.cub_temp, bv.cub_temp_bytes, st));
+    clk_bin.stop();
     STAGE("tile binning");
 
     RenderFwdArgs r;
@@ -231,7 +289,10 @@ int surfel_forward_render(int P, int width, int height, int64_t num_rendered, co
     r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
     r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
     r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
-    launch_render_fwd(r, st);
+    {
+        StageClock clk(st, 3);
+        launch_render_fwd(r, st);
+    }
     STAGE("render forward");
     return 0;
 }
@@ -276,7 +337,10 @@ int surfel_backward(int P, int D, int M, int64_t num_rendered, const float *back
         r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
         r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
         r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = gacc; r.subtile_cull = g_subtile_cull;
-        launch_render_bwd(r, st);
+        {
+            StageClock clk(st, 4);
+            launch_render_bwd(r, st);
+        }
         STAGE("render backward");
     }
 
@@ -291,7 +355,10 @@ int surfel_backward(int P, int D, int M, int64_t num_rendered, const float *back
     a.dL_dmean2D = dL_dmean2D; a.dL_dnormal = dL_dnormal; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
     a.dL_dmean3D = dL_dmean3D; a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale;
     a.dL_drot = dL_drot;
-    launch_preprocess_bwd(a, st);
+    {
+        StageClock clk(st, 5);
+        launch_preprocess_bwd(a, st);
+    }
     STAGE("preprocess backward");
     return 0;
 }
@@ -325,6 +392,23 @@ int surfel_debug_copy_binning(int width, int height, int64_t num_rendered, const
         CK("copy point list", cudaMemcpyAsync(point_list_out, bv.point_list, (size_t)num_rendered * sizeof(uint32_t),
                                               cudaMemcpyDeviceToDevice, st));
     }
+    return 0;
+}
+
+int surfel_debug_copy_geometry(int P, const char *geometry_buffer, uint32_t *tiles_touched_out,
+                               uint32_t *idx_sorted_out, uint32_t *offsets_out, float *records_out, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P <= 0 || !geometry_buffer) return fail("surfel_debug_copy_geometry", "bad arguments");
+    GeomView g = carve_geom(const_cast<char *>(geometry_buffer), P, depth_sort_temp_bytes(P));
+    const size_t n = (size_t)P;
+    if (tiles_touched_out)
+        CK("copy tiles", cudaMemcpyAsync(tiles_touched_out, g.tiles_touched, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (idx_sorted_out)
+        CK("copy idx", cudaMemcpyAsync(idx_sorted_out, g.idx_sorted, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (offsets_out) CK("copy offsets", cudaMemcpyAsync(offsets_out, g.offsets, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (records_out)
+        CK("copy records", cudaMemcpyAsync(records_out, g.rec, n * REC_BYTES, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

@@ -15,6 +15,10 @@ from .. import _lib
 
 NUM_CHANNELS = 3  # RAST/cuda_rasterizer/config.h:15
 
+# tests only: when KEEP_LAST is set, the scratch buffers of the most recent forward stay reachable here
+KEEP_LAST = False
+LAST = None
+
 
 def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:  # same check (and wording) as CHECK_INPUT, rasterize_points.cu:27-29
@@ -77,6 +81,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         _lib.check(L.surfel_forward_render(
             P, W, H, num_rendered, _ptr(background), _ptr(radii), _ptr(geom_buf), _ptr(bin_buf), _ptr(img_buf),
             _ptr(out_color), _ptr(out_others), st, int(bool(debug))), "surfel_forward_render")
+    if KEEP_LAST:
+        global LAST
+        LAST = (num_rendered, geom_buf, bin_buf, img_buf)
     return num_rendered, out_color, out_others, radii, geom_buf, bin_buf, img_buf
 
 
@@ -153,3 +160,18 @@ def debug_binning(width, height, num_rendered, binningBuffer, imageBuffer):
         _lib.check(L.surfel_debug_copy_binning(width, height, num_rendered, _ptr(binningBuffer), _ptr(imageBuffer),
                                                _ptr(ranges), _ptr(plist), _stream()), "surfel_debug_copy_binning")
     return ranges.to(torch.int64) & 0xFFFFFFFF, (plist[:num_rendered].to(torch.int64) & 0xFFFFFFFF)
+
+
+def debug_geometry(P, geomBuffer):
+    """(tiles_touched [P], idx_sorted [P], offsets [P], records [P,20]) copied out of the geometry scratch (tests only)."""
+    L = _lib.lib()
+    dev = geomBuffer.device
+    tiles = torch.empty((P,), dtype=torch.int32, device=dev)
+    idx = torch.empty((P,), dtype=torch.int32, device=dev)
+    offs = torch.empty((P,), dtype=torch.int32, device=dev)
+    recs = torch.empty((P, 20), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.surfel_debug_copy_geometry(P, _ptr(geomBuffer), _ptr(tiles), _ptr(idx), _ptr(offs), _ptr(recs),
+                                                _stream()), "surfel_debug_copy_geometry")
+    m = 0xFFFFFFFF
+    return tiles.to(torch.int64) & m, idx.to(torch.int64) & m, offs.to(torch.int64) & m, recs

@@ -85,16 +85,20 @@ def cam_tilted(width: int, height: int, f: float, yaw: float = 0.2, pitch: float
 
 def _common(P: int, g: torch.Generator, scale_med: float, scale_sig: float, smin: float, smax: float,
             sh_coeffs: int) -> Dict[str, torch.Tensor]:
-    scales = torch.exp(torch.randn(P, 2, generator=g) * scale_sig + math.log(scale_med)).clamp(smin, smax)
-    rot = torch.randn(P, 4, generator=g)
+    # Everything is drawn and transformed in float64 and rounded to float32 once at the end, so that
+    # 1-ulp differences of vectorised float32 exp/sigmoid between hosts or thread counts cannot leak
+    # into the scene (both benchmark arms must see bit-identical inputs; bench.py prints their CRC).
+    f64 = dict(generator=g, dtype=torch.float64)
+    scales = torch.exp(torch.randn(P, 2, **f64) * scale_sig + math.log(scale_med)).clamp(smin, smax)
+    rot = torch.randn(P, 4, **f64)
     rot = rot / rot.norm(dim=1, keepdim=True)
-    opac = torch.sigmoid(torch.randn(P, 1, generator=g) * 1.5)
-    shs = torch.randn(P, sh_coeffs, 3, generator=g)
+    opac = torch.sigmoid(torch.randn(P, 1, **f64) * 1.5)
+    shs = torch.randn(P, sh_coeffs, 3, **f64)
     shs[:, 0, :] *= 0.6
     if sh_coeffs > 1:
         shs[:, 1:, :] *= 0.08
-    return {"scales": scales.contiguous(), "rotations": rot.contiguous(), "opacities": opac.contiguous(),
-            "shs": shs.contiguous()}
+    return {"scales": scales.float().contiguous(), "rotations": rot.float().contiguous(),
+            "opacities": opac.float().contiguous(), "shs": shs.float().contiguous()}
 
 
 def street_scene(P: int, seed: int, sh_degree: int = 3) -> Dict[str, torch.Tensor]:
@@ -103,15 +107,16 @@ def street_scene(P: int, seed: int, sh_degree: int = 3) -> Dict[str, torch.Tenso
     n_g = int(0.4 * P)
     n_f = int(0.4 * P)
     n_c = P - n_g - n_f
-    u = lambda n, a, b: torch.rand(n, generator=g) * (b - a) + a  # noqa: E731
-    ground = torch.stack([u(n_g, -15, 15), 1.6 + 0.02 * torch.randn(n_g, generator=g), u(n_g, 1, 90)], 1)
-    side = (torch.rand(n_f, generator=g) < 0.5).float() * 2 - 1
-    fac = torch.stack([side * (10 + 0.05 * torch.randn(n_f, generator=g)), u(n_f, -10, 1.6), u(n_f, 1, 90)], 1)
+    f64 = dict(generator=g, dtype=torch.float64)
+    u = lambda n, a, b: torch.rand(n, **f64) * (b - a) + a  # noqa: E731
+    ground = torch.stack([u(n_g, -15, 15), 1.6 + 0.02 * torch.randn(n_g, **f64), u(n_g, 1, 90)], 1)
+    side = (torch.rand(n_f, **f64) < 0.5).double() * 2 - 1
+    fac = torch.stack([side * (10 + 0.05 * torch.randn(n_f, **f64)), u(n_f, -10, 1.6), u(n_f, 1, 90)], 1)
     clu = torch.stack([u(n_c, -9, 9), u(n_c, -3, 1.6), u(n_c, 3, 60)], 1)
     xyz = torch.cat([ground, fac, clu], 0)
     out = _common(P, g, 0.03, 0.5, 0.004, 0.4, (sh_degree + 1) ** 2)
     perm = torch.randperm(P, generator=g)
-    out["means3D"] = xyz[perm].contiguous().float()
+    out["means3D"] = xyz[perm].float().contiguous()
     out["sh_degree"] = sh_degree
     return out
 
@@ -119,24 +124,36 @@ def street_scene(P: int, seed: int, sh_degree: int = 3) -> Dict[str, torch.Tenso
 def box_scene(P: int = 10_000, seed: int = 3, sh_degree: int = 0) -> Dict[str, torch.Tensor]:
     """BOX(P, seed): x,y~U(-3,3), z~U(2,10)."""
     g = torch.Generator("cpu").manual_seed(seed)
-    xyz = torch.stack([torch.rand(P, generator=g) * 6 - 3, torch.rand(P, generator=g) * 6 - 3,
-                       torch.rand(P, generator=g) * 8 + 2], 1)
+    f64 = dict(generator=g, dtype=torch.float64)
+    xyz = torch.stack([torch.rand(P, **f64) * 6 - 3, torch.rand(P, **f64) * 6 - 3, torch.rand(P, **f64) * 8 + 2], 1)
     out = _common(P, g, 0.08, 0.4, 0.01, 0.5, (sh_degree + 1) ** 2)
-    out["means3D"] = xyz.contiguous().float()
+    out["means3D"] = xyz.float().contiguous()
     out["sh_degree"] = sh_degree
     return out
+
+
+def scene_crc(scene: Dict[str, torch.Tensor]) -> int:
+    """CRC32 over the raw bytes of every input tensor (identical inputs <=> identical CRC)."""
+    import zlib
+    crc = 0
+    for k in sorted(scene):
+        v = scene[k]
+        if isinstance(v, torch.Tensor):
+            crc = zlib.crc32(v.contiguous().numpy().tobytes(), crc)
+    return crc
 
 
 def upstream_grads(W: int, H: int, mode: str = "color_alpha", seed: int = 100):
     """dL/dcolor [3,H,W] and dL/dallmap [7,H,W] (SURVEY.md 8d 'Upstream gradients')."""
     g = torch.Generator("cpu").manual_seed(seed)
+    f64 = dict(generator=g, dtype=torch.float64)
     HW = W * H
-    d_color = torch.randn(3, H, W, generator=g) / (3 * HW)
+    d_color = (torch.randn(3, H, W, **f64) / (3 * HW)).float()
     d_all = torch.zeros(7, H, W)
     if mode == "color_alpha":
-        d_all[1] = torch.randn(H, W, generator=g) / HW
+        d_all[1] = (torch.randn(H, W, **f64) / HW).float()
     elif mode == "all":
-        d_all = torch.randn(7, H, W, generator=g) / (7 * HW)
+        d_all = (torch.randn(7, H, W, **f64) / (7 * HW)).float()
     elif mode == "color":
         pass
     else:
