@@ -148,7 +148,7 @@ SURFEL_API int surfel_debug_copy_binning(int width, int height, int64_t num_rend
                               uint32_t *ranges_out, uint32_t *point_list_out, void *stream);
 
 /* Debug view of the geometry scratch: per-Gaussian tile counts [P], depth-ordered ids [P], inclusive
- * offsets [P] (all uint32) and the packed 80-byte projected records [P,20] (fp32 words). Any output
+ * offsets [P] (all uint32) and the packed 96-byte projected records [P,24] (fp32 words). Any output
  * may be NULL. */
 SURFEL_API int surfel_debug_copy_geometry(int P, const char *geometry_buffer, uint32_t *tiles_touched_out,
                                           uint32_t *idx_sorted_out, uint32_t *offsets_out, float *records_out,

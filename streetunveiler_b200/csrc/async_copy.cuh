@@ -1,5 +1,5 @@
 // async_copy.cuh -- mbarrier + 1-D bulk async copy (TMA engine, cp.async.bulk) wrappers for sm_100a.
-// Used to gather per-instance 80-B Gaussian records from global/L2 into shared memory while the
+// Used to gather per-instance 96-B Gaussian records from global/L2 into shared memory while the
 // previous batch is being blended (no register staging, completion tracked by transaction bytes).
 #pragma once
 #include <cuda_runtime.h>

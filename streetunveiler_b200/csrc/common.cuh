@@ -21,18 +21,21 @@ constexpr float T_EPS = 0.0001f;              // forward.cu:389
 
 // ---------------------------------------------------------------------------------------------
 // Per-Gaussian projected record: the ONLY thing the two render kernels read per instance.
-// 80 B = 5 x 16 B, 16-B aligned, so one record is one bulk async copy (cp.async.bulk) into smem.
+// 96 B = 6 x 16 B, 16-B aligned, so one record is one bulk async copy (cp.async.bulk) into smem.
 //   q0 = (Tu.x, Tu.y, Tu.z, Tv.x)
 //   q1 = (Tv.y, Tv.z, Tw.x, Tw.y)
 //   q2 = (Tw.z, mean2D.x, mean2D.y, opacity)
 //   q3 = (n.x, n.y, n.z, r)
-//   q4 = (g, b, bbox_x [lo16 = x0, hi16 = x1], bbox_y [lo16 = y0, hi16 = y1])
+//   q4 = (g, b, e.x, e.y)
+//   q5 = (M00, M01, M11, r2)
 // (Tu,Tv,Tw) = rows of the splat->pixel homogeneous map (reference geomState.transMat,
 // rasterizer_impl.h:38), n = view-space normal flipped towards the camera, rgb = SH colour or
-// colors_precomp.  bbox = conservative inclusive pixel bounds of {alpha >= 1/255} used for
-// sub-tile culling (empty when x1 < x0).
+// colors_precomp.  (e, M, r2) is the conservative footprint of {alpha >= 1/255} used for sub-tile
+// culling: the pixel p can only contribute if (p-e)^T M (p-e) <= 1 (perspective-correct ellipse
+// rho3d <= tau) or |p - mean2D|^2 <= r2 (low-pass disc rho2d <= tau), tau = 2 ln(255 opacity)
+// slightly inflated.  M = 0 encodes "cannot bound: always evaluate".
 // ---------------------------------------------------------------------------------------------
-constexpr int REC_FLOATS = 20;
+constexpr int REC_FLOATS = 24;
 constexpr int REC_BYTES = REC_FLOATS * 4;
 
 // Per-Gaussian gradient accumulator written by the backward render kernel and consumed by the
@@ -52,7 +55,7 @@ __host__ __device__ inline T *carve(char *&p, size_t count)
 
 // Private layout of the geometry scratch (forward -> backward state, P-indexed).
 struct GeomView {
-    float *rec;              // [P][20]
+    float *rec;              // [P][REC_FLOATS]
     uint32_t *tiles_touched; // [P]
     uint32_t *depth_key;     // [P]  fp32 bits of view-space z, 0xFFFFFFFF for culled
     uint32_t *depth_key_sorted; // [P]

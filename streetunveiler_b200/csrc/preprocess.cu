@@ -8,9 +8,9 @@
 //
 // The arithmetic keeps the reference's operation order (including glm's column-major product
 // order) because radii / tile rects / sort keys must come out bit-identical; the memory side is
-// new: one thread per Gaussian, 128-bit loads of rotation / SH rows, and ONE packed 80-B record
-// per Gaussian (common.cuh) instead of six separate arrays, plus a conservative alpha>=1/255
-// pixel bounding box used by the render kernels for sub-tile culling.
+// new: one thread per Gaussian, 128-bit loads of rotation / SH rows, and ONE packed 96-B record
+// per Gaussian (common.cuh) instead of six separate arrays, including a conservative alpha>=1/255
+// footprint (ellipse + low-pass disc) used by the render kernels for sub-tile culling.
 #include <cstdio>
 
 #include "common.cuh"
@@ -85,55 +85,61 @@ __device__ __forceinline__ void tile_rect(const float px, const float py, const 
     y1 = min(gy, max(0, (int)((py + max_radius + TILE_Y - 1) / TILE_Y)));
 }
 
-// Conservative inclusive pixel bounds of the region where this splat can reach alpha >= 1/255
-// (rho = min(rho3d, rho2d) <= tau = 2 ln(255 o)); margins absorb fp32 rounding of the conic AABB.
-__device__ __forceinline__ void alpha_bbox(const float Tm[3][3], const float mx, const float my, const float opacity,
-                                           const int W, const int H, uint32_t &bx, uint32_t &by)
+// Conservative footprint of the region where this splat can reach alpha >= 1/255, i.e.
+// rho = min(rho3d, rho2d) <= tau = 2 ln(255 o):
+//   * rho2d <= tau is the disc |p - mean2D|^2 <= tau / 2,
+//   * rho3d <= tau is a conic in pixel space.  With pixel offsets (X,Y) from the projected centre c,
+//     the intersection point is p = a0 X + a1 Y + a2 with a0 = Tv' x Tw, a1 = Tw x Tu', a2 = Tu' x Tv'
+//     (Tu' = Tu - c.x Tw, Tv' = Tv - c.y Tw), and rho3d <= tau <=> p.x^2 + p.y^2 - tau p.z^2 <= 0.
+//     When the quadratic part is positive definite this is an ellipse (X-e)^T M (X-e) <= 1.
+// tau is inflated (x1.002 + 0.01) to absorb fp32 rounding of the per-pixel evaluation; the render
+// kernels additionally inflate the pixel block by half a pixel and accept up to 1.02.
+// out = (e.x, e.y, M00, M01, M11, r2);  M = 0: not boundable, always evaluate;  r2 < 0 and a far-away
+// centre: can never contribute.
+__device__ __forceinline__ void cull_footprint(const float Tm[3][3], const float mx, const float my,
+                                               const float opacity, float out[6])
 {
-    int x0 = 0, x1 = W - 1, y0 = 0, y1 = H - 1;
+    out[0] = mx; out[1] = my; out[2] = 0.f; out[3] = 0.f; out[4] = 0.f; out[5] = 1e30f;  // default: always evaluate
     const float o255 = 255.0f * opacity;
     if (!(o255 >= 1.0f)) {
-        // o * exp(<=0) < 1/255 for every pixel unless rounding interferes: keep a 1-ulp guard
-        if (o255 < 0.999f) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }
-    } else {
-        const float tau = 2.0f * __logf(o255) * 1.002f + 0.01f;
-        // low-pass disc: 2 |d|^2 <= tau
-        const float rl = sqrtf(0.5f * tau) + 0.5f;
-        float lx = mx - rl, hx = mx + rl, ly = my - rl, hy = my + rl;
-        // perspective-correct ellipse u^2+v^2 <= tau: same conic AABB as forward.cu:119-145 with cutoff^2 = tau
-        const float tz2 = Tm[2][2] * Tm[2][2];
-        const float d = tau * (Tm[2][0] * Tm[2][0] + Tm[2][1] * Tm[2][1]) - tz2;
-        bool bounded = d < -1e-3f * tz2;
-        if (bounded) {
-            const float inv = 1.0f / d;
-            const float f0 = tau * inv, f1 = tau * inv, f2 = -inv;
-            const float cx = f0 * Tm[0][0] * Tm[2][0] + f1 * Tm[0][1] * Tm[2][1] + f2 * Tm[0][2] * Tm[2][2];
-            const float cy = f0 * Tm[1][0] * Tm[2][0] + f1 * Tm[1][1] * Tm[2][1] + f2 * Tm[1][2] * Tm[2][2];
-            const float qx = f0 * Tm[0][0] * Tm[0][0] + f1 * Tm[0][1] * Tm[0][1] + f2 * Tm[0][2] * Tm[0][2];
-            const float qy = f0 * Tm[1][0] * Tm[1][0] + f1 * Tm[1][1] * Tm[1][1] + f2 * Tm[1][2] * Tm[1][2];
-            const float hx2 = cx * cx - qx, hy2 = cy * cy - qy;
-            if (hx2 == hx2 && hy2 == hy2 && fabsf(cx) < 1e7f && fabsf(cy) < 1e7f) {
-                // fp32 cancellation in c^2 - q: |error| <= ~1e-6 (c^2 + |q|); plus relative and absolute slack
-                const float sx2 = 1e-6f * (cx * cx + fabsf(qx)), sy2 = 1e-6f * (cy * cy + fabsf(qy));
-                const float ex = sqrtf(fmaxf(hx2 + sx2, 0.f)) * 1.002f + 0.75f;
-                const float ey = sqrtf(fmaxf(hy2 + sy2, 0.f)) * 1.002f + 0.75f;
-                lx = fminf(lx, cx - ex); hx = fmaxf(hx, cx + ex);
-                ly = fminf(ly, cy - ey); hy = fmaxf(hy, cy + ey);
-            } else {
-                bounded = false;
-            }
+        if (o255 < 0.999f) {  // o exp(<=0) < 1/255 for every pixel (1e-3 guard against rounding of the product)
+            out[0] = -1e30f; out[1] = -1e30f; out[2] = 1.f; out[4] = 1.f; out[5] = -1.f;
         }
-        if (bounded) {
-            x0 = (int)fmaxf(floorf(lx), 0.f);
-            y0 = (int)fmaxf(floorf(ly), 0.f);
-            x1 = (int)fminf(ceilf(hx), (float)(W - 1));
-            y1 = (int)fminf(ceilf(hy), (float)(H - 1));
-            if (x1 < x0 || y1 < y0) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }
-        }
+        return;
     }
-    x0 = min(x0, 65535); x1 = min(x1, 65535); y0 = min(y0, 65535); y1 = min(y1, 65535);
-    bx = (uint32_t)x0 | ((uint32_t)x1 << 16);
-    by = (uint32_t)y0 | ((uint32_t)y1 << 16);
+    const float tau = 2.0f * __logf(o255) * 1.002f + 0.01f;
+    const float Tw[3] = {Tm[2][0], Tm[2][1], Tm[2][2]};
+    float Tu[3], Tv[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        Tu[i] = Tm[0][i] - mx * Tw[i];
+        Tv[i] = Tm[1][i] - my * Tw[i];
+    }
+    const float a0[3] = {Tv[1] * Tw[2] - Tv[2] * Tw[1], Tv[2] * Tw[0] - Tv[0] * Tw[2], Tv[0] * Tw[1] - Tv[1] * Tw[0]};
+    const float a1[3] = {Tw[1] * Tu[2] - Tw[2] * Tu[1], Tw[2] * Tu[0] - Tw[0] * Tu[2], Tw[0] * Tu[1] - Tw[1] * Tu[0]};
+    const float a2[3] = {Tu[1] * Tv[2] - Tu[2] * Tv[1], Tu[2] * Tv[0] - Tu[0] * Tv[2], Tu[0] * Tv[1] - Tu[1] * Tv[0]};
+    const float q00 = a0[0] * a0[0] + a0[1] * a0[1] - tau * a0[2] * a0[2];
+    const float q01 = a0[0] * a1[0] + a0[1] * a1[1] - tau * a0[2] * a1[2];
+    const float q11 = a1[0] * a1[0] + a1[1] * a1[1] - tau * a1[2] * a1[2];
+    const float q02 = a0[0] * a2[0] + a0[1] * a2[1] - tau * a0[2] * a2[2];
+    const float q12 = a1[0] * a2[0] + a1[1] * a2[1] - tau * a1[2] * a2[2];
+    const float q22 = a2[0] * a2[0] + a2[1] * a2[1] - tau * a2[2] * a2[2];
+    const float det = q00 * q11 - q01 * q01;
+    // positive definite with a comfortable margin, otherwise the conic is (nearly) unbounded
+    if (!(q00 > 0.f && q11 > 0.f && det > 1e-4f * q00 * q11)) return;
+    const float inv = 1.0f / det;
+    const float ex = (q01 * q12 - q11 * q02) * inv;
+    const float ey = (q01 * q02 - q00 * q12) * inv;
+    const float fmin = q22 + q02 * ex + q12 * ey;
+    if (!(fabsf(ex) < 1e6f && fabsf(ey) < 1e6f) || !(fmin == fmin)) return;
+    out[5] = 0.5f * tau;
+    if (!(fmin < 0.f)) {  // empty ellipse: only the low-pass disc can contribute
+        out[0] = -1e30f; out[1] = -1e30f; out[2] = 1.f; out[4] = 1.f;
+        return;
+    }
+    const float s = -1.0f / fmin;
+    out[0] = mx + ex; out[1] = my + ey;
+    out[2] = q00 * s; out[3] = q01 * s; out[4] = q11 * s;
 }
 
 // =============================================================================================
@@ -283,15 +289,16 @@ preprocess_fwd_kernel(const int P, const int D, const int M, const float *__rest
         }
 
         const float opacity = opacities[idx];
-        uint32_t bx, by;
-        alpha_bbox(Tm, cx, cy, opacity, W, H, bx, by);
+        float fp[6];
+        cull_footprint(Tm, cx, cy, opacity, fp);
 
         float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)idx * REC_FLOATS);
         r4[0] = make_float4(Tm[0][0], Tm[0][1], Tm[0][2], Tm[1][0]);
         r4[1] = make_float4(Tm[1][1], Tm[1][2], Tm[2][0], Tm[2][1]);
         r4[2] = make_float4(Tm[2][2], cx, cy, opacity);
         r4[3] = make_float4(normal.x, normal.y, normal.z, rgb[0]);
-        r4[4] = make_float4(rgb[1], rgb[2], __uint_as_float(bx), __uint_as_float(by));
+        r4[4] = make_float4(rgb[1], rgb[2], fp[0], fp[1]);
+        r4[5] = make_float4(fp[2], fp[3], fp[4], fp[5]);
         clamped[idx] = (uint8_t)clamp_bits;
 
         radius_out = (int)radius;

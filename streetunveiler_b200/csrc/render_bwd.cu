@@ -7,20 +7,18 @@
 //
 // What is different from the reference kernel (which issues up to 16 scalar float atomicAdds per
 // contributing pixel-instance, backward.cu:339-443):
-//   * the same packed 80-B records / TMA bulk gather / 8x4-pixel warp blocks / per-warp batch
-//     compaction as the forward kernel, plus a per-tile bound (max last contributor, saved by the
-//     forward) so the list tail nobody blended is never even loaded;
+//   * the same packed 96-B records / producer-warp TMA ring / 8x4-pixel warp blocks / per-warp chunk
+//     compaction as the forward kernel (tile_pipeline.cuh), plus a per-tile bound (max last
+//     contributor, saved by the forward) so the list tail nobody blended is never even loaded;
 //   * the 18 per-instance gradient values are summed over the warp's 32 pixels with a
 //     multi-value butterfly (20 shuffles for all 18 values, not 18 x 5), leaving one value per
 //     lane, and flushed with ONE reduction instruction per (warp, instance) into an 80-B
 //     per-Gaussian accumulator record that the backward-preprocess kernel consumes.
-#include "async_copy.cuh"
-#include "common.cuh"
 #include "kernels.h"
+#include "tile_pipeline.cuh"
 
 namespace surfel {
 
-constexpr int BWD_BATCH = 256;
 constexpr int NV = 18;  // gradient values per instance
 
 // Multi-value warp reduction: N values per lane in, one fully reduced value per lane out.
@@ -54,7 +52,7 @@ struct Butterfly {
 };
 
 template <bool CULL>
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(96)
 render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
                   const float *__restrict__ bg, const float *__restrict__ final_Ts,
@@ -62,45 +60,34 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                   const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dothers,
                   float *__restrict__ gacc)
 {
-    __shared__ __align__(128) float s_rec[2][BWD_BATCH * REC_FLOATS];
-    __shared__ uint32_t s_id[2][BWD_BATCH];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(128) TileRing ring;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
+    const uint2 range = ranges[tile];
+    // only list positions [0, total) can have been blended by some pixel of this tile
+    const int total = min((int)(range.y - range.x), (int)tile_max_contrib[tile]);
+    const int nchunks = (total + CHUNK - 1) / CHUNK;
+    if (nchunks == 0) return;
+
+    ring_init(ring, tid);
+
+    if (warp == CONSUMER_WARPS) {
+        // producer: stream slot i <-> list position total-1-i (back to front)
+        const uint32_t last = range.x + (uint32_t)(total - 1);
+        ring_produce<true>(ring, lane, total, point_list, rec, [last](int i) { return last - (uint32_t)i; });
+        return;
+    }
+
     const int tile_x = tile % gx, tile_y = tile / gx;
     const int bx0 = tile_x * TILE_X + (warp & 1) * 8, by0 = tile_y * TILE_Y + (warp >> 1) * 4;
     const uint32_t pix_x = bx0 + (lane & 7), pix_y = by0 + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const float2 pixf = make_float2((float)pix_x, (float)pix_y);
+    const float rx0 = (float)bx0 - 0.5f, rx1 = (float)bx0 + 7.5f, ry0 = (float)by0 - 0.5f, ry1 = (float)by0 + 3.5f;
     const size_t HW = (size_t)W * H;
     const size_t pix_id = (size_t)W * pix_y + pix_x;
-
-    const uint2 range = ranges[tile];
-    // only list positions [0, total) can have been blended by some pixel of this tile
-    const int total = min((int)(range.y - range.x), (int)tile_max_contrib[tile]);
-    const int nbatch = (total + BWD_BATCH - 1) / BWD_BATCH;
-    if (nbatch == 0) return;
-
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // batch b, slot t  <->  list position  total - 1 - (b*BATCH + t)   (back to front)
-    auto issue = [&](int b) {
-        const int n = min(BWD_BATCH, total - b * BWD_BATCH);
-        const int buf = b & 1;
-        if (tid == 0) mbar_arrive_expect_tx(&s_bar[buf], (uint32_t)n * REC_BYTES);
-        if (tid < n) {
-            const uint32_t id = point_list[range.x + (total - 1 - (b * BWD_BATCH + tid))];
-            s_id[buf][tid] = id;
-            bulk_g2s(&s_rec[buf][tid * REC_FLOATS], rec + (size_t)id * REC_FLOATS, REC_BYTES, &s_bar[buf]);
-        }
-    };
 
     const float T_final = inside ? final_Ts[pix_id] : 0;
     float T = T_final;
@@ -123,12 +110,11 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
         dL_dpixel[1] = dL_dpixels[HW + pix_id];
         dL_dpixel[2] = dL_dpixels[2 * HW + pix_id];
     }
-    float last_depth = 0.f, accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
-    float last_normal[3] = {0.f, 0.f, 0.f}, accum_normal_rec[3] = {0.f, 0.f, 0.f};
+    float accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
+    float accum_normal_rec[3] = {0.f, 0.f, 0.f};
     const float final_D = inside ? final_Ts[pix_id + HW] : 0;
     const float final_D2 = inside ? final_Ts[pix_id + 2 * HW] : 0;
     const float final_A = 1 - T_final;
-    float last_alpha = 0.f, last_color[3] = {0.f, 0.f, 0.f};
     float bg_dot_dpixel = 0;
 #pragma unroll
     for (int i = 0; i < 3; i++) bg_dot_dpixel += bg[i] * dL_dpixel[i];
@@ -140,21 +126,19 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
 
     const int my_slot = Butterfly<NV, 4>::slot(lane, 0, NV);
 
-    issue(0);
-    __syncthreads();  // s_id[0] visible (later batches are published by the end-of-iteration barrier)
-    uint32_t phase[2] = {0u, 0u};
-
-    for (int b = 0; b < nbatch; b++) {
-        const int buf = b & 1;
-        if (b + 1 < nbatch) issue(b + 1);
-        mbar_wait(&s_bar[buf], phase[buf]);
-        phase[buf] ^= 1u;
-
-        const int n = min(BWD_BATCH, total - b * BWD_BATCH);
-        const float *sb = s_rec[buf];
-        for (int c = 0; c < n; c += 32) {
-            // chunk slot (c + lane) holds list position pos_first - lane (descending)
-            const int pos_first = total - 1 - (b * BWD_BATCH + c);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int cb = 0; cb < nchunks; cb++) {
+        const int n = min(CHUNK, total - cb * CHUNK);
+        // chunk slot s holds list position pos0 - s (descending); skip chunks entirely behind this warp's pixels
+        const int pos0 = total - 1 - cb * CHUNK;
+        const bool chunk_live = (uint32_t)(pos0 - (n - 1)) < warp_last;
+        // Always wait for the stage, even when skipping it: arriving on `empty` without having observed
+        // `full` would let this warp lap the ring and double-count in a phase other warps still read.
+        mbar_wait(&ring.full[stage], phase);
+        const float *sb = ring.rec[stage];
+        for (int c = 0; chunk_live && c < n; c += 32) {
+            const int pos_first = pos0 - c;
             const int pos_min = pos_first - (min(32, n - c) - 1);
             if ((uint32_t)pos_min >= warp_last) continue;  // entirely behind everything this warp blended
             uint32_t mask;
@@ -164,11 +148,7 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                 if (j < n) {
                     const int pos = pos_first - lane;
                     hit = (uint32_t)pos < warp_last;
-                    if (CULL && hit) {
-                        const uint2 bb = *reinterpret_cast<const uint2 *>(sb + j * REC_FLOATS + 18);
-                        const int x0 = bb.x & 0xffff, x1 = bb.x >> 16, y0 = bb.y & 0xffff, y1 = bb.y >> 16;
-                        hit = (x0 <= bx0 + 7) && (x1 >= bx0) && (y0 <= by0 + 3) && (y1 >= by0);
-                    }
+                    if (CULL && hit) hit = block_may_contribute(sb + j * REC_FLOATS, rx0, rx1, ry0, ry1);
                 }
                 mask = __ballot_sync(0xffffffffu, hit);
             }
@@ -206,19 +186,24 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                             const float alpha = fminf(0.99f, opa * G);
                             if (!(alpha < ALPHA_MIN)) {
                                 valid = true;
-                                const float4 q3 = r4[3], q4 = r4[4];
+                                const float4 q3 = r4[3];
+                                const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
                                 const float normal[3] = {q3.x, q3.y, q3.z};
                                 const float col[3] = {q3.w, q4.x, q4.y};
 
+                                // The reference keeps (last_alpha, last_color, ...) and folds them into the
+                                // suffix accumulators at the NEXT contributor (backward.cu:329,365-374); folding
+                                // them right after use is the same arithmetic on the same operands, with 8 fewer
+                                // live registers.
                                 T = T / (1.f - alpha);
                                 const float w = alpha * T;
+                                const float one_m_alpha = 1.f - alpha;
                                 float dL_dalpha = 0.0f;
 #pragma unroll
                                 for (int ch = 0; ch < 3; ch++) {
                                     const float cc = col[ch];
-                                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                                    last_color[ch] = cc;
                                     dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
+                                    accum_rec[ch] = alpha * cc + one_m_alpha * accum_rec[ch];
                                     v[12 + ch] = w * dL_dpixel[ch];
                                 }
                                 float dL_dz = 0.0f;
@@ -232,21 +217,17 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                                 const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
                                 dL_dz += dL_dmd * dmd_dd;
 
-                                accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
-                                last_depth = c_d;
                                 dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-                                accum_alpha_rec = last_alpha * 1.0 + (1.f - last_alpha) * accum_alpha_rec;
+                                accum_depth_rec = alpha * c_d + one_m_alpha * accum_depth_rec;
                                 dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
+                                accum_alpha_rec = alpha * 1.0 + one_m_alpha * accum_alpha_rec;
 #pragma unroll
                                 for (int ch = 0; ch < 3; ch++) {
-                                    accum_normal_rec[ch] =
-                                        last_alpha * last_normal[ch] + (1.f - last_alpha) * accum_normal_rec[ch];
-                                    last_normal[ch] = normal[ch];
                                     dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
+                                    accum_normal_rec[ch] = alpha * normal[ch] + one_m_alpha * accum_normal_rec[ch];
                                     v[15 + ch] = alpha * T * dL_dnormal2D[ch];
                                 }
                                 dL_dalpha *= T;
-                                last_alpha = alpha;
                                 dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
 
                                 const float dL_dG = opa * dL_dalpha;
@@ -283,11 +264,13 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                 }
                 if (__any_sync(0xffffffffu, valid)) {
                     Butterfly<NV, 4>::run(v, lane);
-                    if (my_slot >= 0) atomicAdd(gacc + (size_t)s_id[buf][jj] * GACC_FLOATS + my_slot, v[0]);
+                    if (my_slot >= 0) atomicAdd(gacc + (size_t)ring.id[stage][jj] * GACC_FLOATS + my_slot, v[0]);
                 }
             }
         }
-        __syncthreads();  // all warps finished with this buffer before it is refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.empty[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
     }
 }
 
@@ -296,11 +279,11 @@ void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
     const int tiles = a.gx * a.gy;
     if (tiles == 0) return;
     if (a.subtile_cull)
-        render_bwd_kernel<true><<<tiles, 256, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
+        render_bwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
                                                            a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
                                                            a.dL_dothers, a.gacc);
     else
-        render_bwd_kernel<false><<<tiles, 256, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
+        render_bwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
                                                             a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
                                                             a.dL_dothers, a.gacc);
 }

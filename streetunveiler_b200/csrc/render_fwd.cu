@@ -2,70 +2,62 @@
 //
 // Behavioural specification: RAST/cuda_rasterizer/forward.cu:256-448 (renderCUDA) -- the per-pixel
 // recurrence is restated in SURVEY.md Appendix A and kept in the reference's operation order so
-// the integer decisions (alpha < 1/255, T(1-alpha) < 1e-4, T > 0.5) fall identically.
+// the integer decisions (alpha < 1/255, T(1-alpha) < 1e-4, T > 0.5) fall identically (the forward
+// outputs are bit-identical to the reference extension on the same GPU; tests check it).
 //
 // What is different from the reference kernel:
-//   * one packed 80-B record per instance, gathered into shared memory by the TMA engine
-//     (cp.async.bulk + mbarrier transaction bytes), double-buffered so batch b+1 streams in while
-//     batch b is blended; colour lives in the record (the reference re-reads it from global memory
-//     inside the inner loop, forward.cu:418);
-//   * each warp owns an 8x4 pixel block of the 16x16 tile and first *compacts* the batch: 32
-//     instances are tested in parallel (one per lane) against the warp's block using the
-//     conservative alpha>=1/255 bounding box from preprocess; only surviving instances are
-//     evaluated by the 32 pixels.  Skipped instances can never pass the reference's alpha test,
-//     so results are unchanged (tests compare culling on/off bit-for-bit);
-//   * warp-granular early-out (a warp whose 32 pixels are saturated stops evaluating).
-#include "async_copy.cuh"
-#include "common.cuh"
+//   * one packed 96-B record per instance, gathered into shared memory by the TMA engine
+//     (cp.async.bulk + mbarrier transaction bytes) by a dedicated producer warp through a
+//     6-stage ring (tile_pipeline.cuh); colour lives in the record (the reference re-reads it from
+//     global memory inside the inner loop, forward.cu:418); no __syncthreads per batch;
+//   * each consumer warp owns an 8x4 pixel block of the 16x16 tile and first *compacts* each chunk:
+//     32 instances are tested in parallel (one per lane) against the warp's block using the
+//     conservative alpha >= 1/255 footprint from preprocess (ellipse + low-pass disc); only
+//     surviving instances are evaluated by the 32 pixels.  Skipped instances can never pass the
+//     reference's alpha test, so results are unchanged (tests compare culling on/off bit-for-bit);
+//   * warp-granular early-out: a warp whose 32 pixels are saturated stops evaluating, and the
+//     producer stops streaming once all eight warps are.
 #include "kernels.h"
+#include "tile_pipeline.cuh"
 
 namespace surfel {
 
-constexpr int FWD_BATCH = 256;
-
 template <bool CULL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TILE_THREADS)
 render_fwd_kernel(const int W, const int H, const int gx, const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
                   const float *__restrict__ bg, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
                   uint32_t *__restrict__ tile_max_contrib, float *__restrict__ out_color,
                   float *__restrict__ out_others)
 {
-    __shared__ __align__(128) float s_rec[2][FWD_BATCH * REC_FLOATS];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(128) TileRing ring;
     __shared__ uint32_t s_max_contrib;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+    const int nchunks = (total + CHUNK - 1) / CHUNK;
+
+    if (tid == 0) s_max_contrib = 0;
+    ring_init(ring, tid);
+
+    if (warp == CONSUMER_WARPS) {
+        // ------------------------------ producer warp ------------------------------
+        const uint32_t base = range.x;
+        ring_produce<false>(ring, lane, total, point_list, rec, [base](int i) { return base + (uint32_t)i; });
+        __syncthreads();
+        return;
+    }
+
+    // ------------------------------ consumer warps ------------------------------
     const int tile_x = tile % gx, tile_y = tile / gx;
-    // warp -> 8x4 pixel block, lane -> pixel inside it
     const int bx0 = tile_x * TILE_X + (warp & 1) * 8, by0 = tile_y * TILE_Y + (warp >> 1) * 4;
     const uint32_t pix_x = bx0 + (lane & 7), pix_y = by0 + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const float2 pixf = make_float2((float)pix_x, (float)pix_y);
-
-    const uint2 range = ranges[tile];
-    const int total = (int)(range.y - range.x);
-    const int nbatch = (total + FWD_BATCH - 1) / FWD_BATCH;
-
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-        s_max_contrib = 0;
-    }
-    __syncthreads();
-
-    auto issue = [&](int b) {
-        const int n = min(FWD_BATCH, total - b * FWD_BATCH);
-        const int buf = b & 1;
-        if (tid == 0) mbar_arrive_expect_tx(&s_bar[buf], (uint32_t)n * REC_BYTES);
-        if (tid < n) {
-            const uint32_t id = point_list[range.x + b * FWD_BATCH + tid];
-            bulk_g2s(&s_rec[buf][tid * REC_FLOATS], rec + (size_t)id * REC_FLOATS, REC_BYTES, &s_bar[buf]);
-        }
-    };
+    const float rx0 = (float)bx0 - 0.5f, rx1 = (float)bx0 + 7.5f, ry0 = (float)by0 - 0.5f, ry1 = (float)by0 + 3.5f;
 
     bool done = !inside;
     float T = 1.0f;
@@ -73,81 +65,77 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
     float Dacc = 0.f, M1 = 0.f, M2 = 0.f, distortion = 0.f, median_depth = 0.f;
     uint32_t last_contributor = 0, median_contributor = 0;  // float -1 -> u32 saturates to 0 (quirk 8)
 
-    if (nbatch > 0) issue(0);
-    uint32_t phase[2] = {0u, 0u};
     bool warp_done = __all_sync(0xffffffffu, done);
+    if (warp_done && lane == 0) atomicAdd(const_cast<int *>(&ring.done_warps), 1);
 
-    for (int b = 0; b < nbatch; b++) {
-        const int buf = b & 1;
-        if (b + 1 < nbatch) issue(b + 1);
-        mbar_wait(&s_bar[buf], phase[buf]);
-        phase[buf] ^= 1u;
-
-        const int n = min(FWD_BATCH, total - b * FWD_BATCH);
-        const float *sb = s_rec[buf];
-        for (int c = 0; c < n && !warp_done; c += 32) {
-            uint32_t mask;
-            if (CULL) {
-                const int j = c + lane;
-                bool hit = false;
-                if (j < n) {
-                    const uint2 bb = *reinterpret_cast<const uint2 *>(sb + j * REC_FLOATS + 18);
-                    const int x0 = bb.x & 0xffff, x1 = bb.x >> 16, y0 = bb.y & 0xffff, y1 = bb.y >> 16;
-                    hit = (x0 <= bx0 + 7) && (x1 >= bx0) && (y0 <= by0 + 3) && (y1 >= by0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int c = 0; c < nchunks; c++) {
+        if (!warp_done) {
+            mbar_wait(&ring.full[stage], phase);
+            const int n = min(CHUNK, total - c * CHUNK);
+            const float *sb = ring.rec[stage];
+#pragma unroll 1
+            for (int h = 0; h < n; h += 32) {
+                uint32_t mask;
+                if (CULL) {
+                    const int j = h + lane;
+                    const bool hit = (j < n) && block_may_contribute(sb + j * REC_FLOATS, rx0, rx1, ry0, ry1);
+                    mask = __ballot_sync(0xffffffffu, hit);
+                } else {
+                    mask = (n - h >= 32) ? 0xffffffffu : ((1u << (n - h)) - 1u);
                 }
-                mask = __ballot_sync(0xffffffffu, hit);
-            } else {
-                mask = (n - c >= 32) ? 0xffffffffu : ((1u << (n - c)) - 1u);
-            }
-            while (mask) {
-                const int jj = c + __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (!done) {
-                    const float4 *r4 = reinterpret_cast<const float4 *>(sb + jj * REC_FLOATS);
-                    const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
-                    const float3 Tu = make_float3(q0.x, q0.y, q0.z);
-                    const float3 Tv = make_float3(q0.w, q1.x, q1.y);
-                    const float3 Tw = make_float3(q1.z, q1.w, q2.x);
-                    // two homogeneous planes through the pixel, intersected with the splat plane
-                    const float3 k = make_float3(pixf.x * Tw.x - Tu.x, pixf.x * Tw.y - Tu.y, pixf.x * Tw.z - Tu.z);
-                    const float3 l = make_float3(pixf.y * Tw.x - Tv.x, pixf.y * Tw.y - Tv.y, pixf.y * Tw.z - Tv.z);
-                    const float3 p = make_float3(k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x);
-                    if (p.z != 0.0f) {
-                        const float2 s = make_float2(p.x / p.z, p.y / p.z);
-                        const float rho3d = (s.x * s.x + s.y * s.y);
-                        const float2 d = make_float2(q2.y - pixf.x, q2.z - pixf.y);
-                        const float rho2d = FILTER_INV_SQUARE * (d.x * d.x + d.y * d.y);
-                        const float rho = fminf(rho3d, rho2d);
-                        const float depth = (s.x * Tw.x + s.y * Tw.y) + Tw.z;
-                        const float power = -0.5f * rho;
-                        if (!(depth < NEAR_N) && !(power > 0.0f)) {
-                            const float alpha = fminf(0.99f, q2.w * expf(power));
-                            if (!(alpha < ALPHA_MIN)) {
-                                const float test_T = T * (1 - alpha);
-                                if (test_T < T_EPS) {
-                                    done = true;
-                                } else {
-                                    const float4 q3 = r4[3], q4 = r4[4];
-                                    const uint32_t contributor = (uint32_t)(b * FWD_BATCH + jj + 1);
-                                    const float w = alpha * T;
-                                    const float A = 1 - T;
-                                    const float m = FAR_N / (FAR_N - NEAR_N) * (1 - NEAR_N / depth);
-                                    distortion += (m * m * A + M2 - 2 * m * M1) * w;
-                                    Dacc += depth * w;
-                                    M1 += m * w;
-                                    M2 += m * m * w;
-                                    if (T > 0.5f) {
-                                        median_depth = depth;
-                                        median_contributor = contributor;
+                while (mask) {
+                    const int jj = h + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (!done) {
+                        const float4 *r4 = reinterpret_cast<const float4 *>(sb + jj * REC_FLOATS);
+                        const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
+                        const float3 Tu = make_float3(q0.x, q0.y, q0.z);
+                        const float3 Tv = make_float3(q0.w, q1.x, q1.y);
+                        const float3 Tw = make_float3(q1.z, q1.w, q2.x);
+                        // two homogeneous planes through the pixel, intersected with the splat plane
+                        const float3 k = make_float3(pixf.x * Tw.x - Tu.x, pixf.x * Tw.y - Tu.y, pixf.x * Tw.z - Tu.z);
+                        const float3 l = make_float3(pixf.y * Tw.x - Tv.x, pixf.y * Tw.y - Tv.y, pixf.y * Tw.z - Tv.z);
+                        const float3 p = make_float3(k.y * l.z - k.z * l.y, k.z * l.x - k.x * l.z, k.x * l.y - k.y * l.x);
+                        if (p.z != 0.0f) {
+                            const float2 s = make_float2(p.x / p.z, p.y / p.z);
+                            const float rho3d = (s.x * s.x + s.y * s.y);
+                            const float2 d = make_float2(q2.y - pixf.x, q2.z - pixf.y);
+                            const float rho2d = FILTER_INV_SQUARE * (d.x * d.x + d.y * d.y);
+                            const float rho = fminf(rho3d, rho2d);
+                            const float depth = (s.x * Tw.x + s.y * Tw.y) + Tw.z;
+                            const float power = -0.5f * rho;
+                            if (!(depth < NEAR_N) && !(power > 0.0f)) {
+                                const float alpha = fminf(0.99f, q2.w * expf(power));
+                                if (!(alpha < ALPHA_MIN)) {
+                                    const float test_T = T * (1 - alpha);
+                                    if (test_T < T_EPS) {
+                                        done = true;
+                                    } else {
+                                        const float4 q3 = r4[3];
+                                        const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
+                                        const uint32_t contributor = (uint32_t)(c * CHUNK + jj + 1);
+                                        const float w = alpha * T;
+                                        const float A = 1 - T;
+                                        const float m = FAR_N / (FAR_N - NEAR_N) * (1 - NEAR_N / depth);
+                                        distortion += (m * m * A + M2 - 2 * m * M1) * w;
+                                        Dacc += depth * w;
+                                        M1 += m * w;
+                                        M2 += m * m * w;
+                                        if (T > 0.5f) {
+                                            median_depth = depth;
+                                            median_contributor = contributor;
+                                        }
+                                        N[0] += q3.x * w;
+                                        N[1] += q3.y * w;
+                                        N[2] += q3.z * w;
+                                        C[0] += q3.w * w;
+                                        C[1] += q4.x * w;
+                                        C[2] += q4.y * w;
+                                        T = test_T;
+                                        last_contributor = contributor;
                                     }
-                                    N[0] += q3.x * w;
-                                    N[1] += q3.y * w;
-                                    N[2] += q3.z * w;
-                                    C[0] += q3.w * w;
-                                    C[1] += q4.x * w;
-                                    C[2] += q4.y * w;
-                                    T = test_T;
-                                    last_contributor = contributor;
                                 }
                             }
                         }
@@ -158,13 +146,13 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                     break;
                 }
             }
-        }
-        // all warps finished reading this buffer; also the block-wide early-out vote
-        const int num_done = __syncthreads_count(done);
-        if (num_done == TILE_PIX) {
-            if (b + 1 < nbatch) mbar_wait(&s_bar[(b + 1) & 1], phase[(b + 1) & 1]);  // drain in-flight copies
+            if (warp_done && lane == 0) atomicAdd(const_cast<int *>(&ring.done_warps), 1);
+        } else if (!ring_wait_or_quit(ring, lane, stage, phase, c)) {
             break;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.empty[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
     }
 
     // per-tile maximum of last_contributor: lets the backward pass skip the untouched list tail
@@ -201,13 +189,13 @@ void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream)
     const int tiles = a.gx * a.gy;
     if (tiles == 0) return;
     if (a.subtile_cull)
-        render_fwd_kernel<true><<<tiles, 256, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
-                                                           a.final_T, a.n_contrib, a.tile_max_contrib, a.out_color,
-                                                           a.out_others);
+        render_fwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec,
+                                                                    a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
+                                                                    a.out_color, a.out_others);
     else
-        render_fwd_kernel<false><<<tiles, 256, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
-                                                            a.final_T, a.n_contrib, a.tile_max_contrib, a.out_color,
-                                                            a.out_others);
+        render_fwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec,
+                                                                     a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
+                                                                     a.out_color, a.out_others);
 }
 
 }  // namespace surfel

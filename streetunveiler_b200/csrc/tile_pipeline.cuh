@@ -1,0 +1,151 @@
+// tile_pipeline.cuh -- shared machinery of the two tile-blend kernels (render_fwd.cu / render_bwd.cu).
+//
+// One CTA per 16x16 tile: 8 consumer warps (each owns an 8x4 pixel block) + 1 producer warp.
+// The tile's depth-ordered instance list is streamed through a ring of NSTAGE shared-memory stages
+// of CHUNK records each.  The producer warp gathers the 96-B records with the TMA engine
+// (cp.async.bulk, completion counted in transaction bytes on the stage's `full` mbarrier); each
+// consumer warp releases a stage by arriving on its `empty` mbarrier.  There is no CTA-wide barrier
+// in the steady state, so a warp whose pixel block is covered by few splats runs ahead of a busy
+// one by up to NSTAGE*CHUNK instances instead of idling at a __syncthreads per batch.
+#pragma once
+#include "async_copy.cuh"
+#include "common.cuh"
+
+namespace surfel {
+
+constexpr int CHUNK = 64;            // records per stage
+constexpr int NSTAGE = 6;            // 6 * 64 * 96 B = 36 KB of records in flight per CTA
+constexpr int CONSUMER_WARPS = 8;
+constexpr int TILE_THREADS = (CONSUMER_WARPS + 1) * 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+struct TileRing {
+    float rec[NSTAGE][CHUNK * REC_FLOATS];
+    uint32_t id[NSTAGE][CHUNK];
+    uint64_t full[NSTAGE];
+    uint64_t empty[NSTAGE];
+    volatile int done_warps;  // consumer warps whose 32 pixels are all saturated (forward early-out)
+    volatile int limit;       // chunks the producer will ever issue (lowered when every warp is done)
+};
+
+__device__ __forceinline__ void ring_init(TileRing &r, const int tid)
+{
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(&r.full[s], 32);               // every producer lane arrives (lane 0 with expect_tx)
+            mbar_init(&r.empty[s], CONSUMER_WARPS);  // one arrival per consumer warp
+        }
+        r.done_warps = 0;
+        r.limit = 0x7fffffff;
+        mbar_fence_init();
+    }
+    __syncthreads();
+}
+
+// Producer warp body.  position(i) maps the i-th streamed slot to an index into point_list
+// (front-to-back for the forward, back-to-front for the backward).
+template <bool STORE_IDS, typename PosFn>
+__device__ __forceinline__ void ring_produce(TileRing &r, const int lane, const int total, const uint32_t *__restrict__ point_list,
+                                             const float *__restrict__ rec, PosFn position)
+{
+    const int nchunks = (total + CHUNK - 1) / CHUNK;
+    int stage = 0;
+    uint32_t ephase = 1;  // parity of the *previous* phase of `empty`: passes immediately on the first lap
+    int issued = 0;
+    for (int c = 0; c < nchunks; c++) {
+        int stop = (lane == 0 && r.done_warps >= CONSUMER_WARPS) ? 1 : 0;
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        if (stop) break;
+        mbar_wait(&r.empty[stage], ephase);
+        const int n = min(CHUNK, total - c * CHUNK);
+#pragma unroll
+        for (int s = lane; s < CHUNK; s += 32) {
+            if (s < n) {
+                const uint32_t g = point_list[position(c * CHUNK + s)];
+                if (STORE_IDS) r.id[stage][s] = g;
+                bulk_g2s(&r.rec[stage][s * REC_FLOATS], rec + (size_t)g * REC_FLOATS, REC_BYTES, &r.full[stage]);
+            }
+        }
+        if (lane == 0)
+            mbar_arrive_expect_tx(&r.full[stage], (uint32_t)n * REC_BYTES);
+        else
+            mbar_arrive(&r.full[stage]);
+        issued = c + 1;
+        if (++stage == NSTAGE) { stage = 0; ephase ^= 1u; }
+    }
+    if (lane == 0) {
+        r.limit = issued;
+        __threadfence_block();
+    }
+    // bulk copies still in flight must land before the CTA may exit (its smem could be re-assigned)
+    const int first = issued > NSTAGE ? issued - NSTAGE : 0;
+    for (int c = first; c < issued; c++) mbar_wait(&r.full[c % NSTAGE], (uint32_t)((c / NSTAGE) & 1));
+}
+
+// Consumer side: wait until stage data landed.  A warp that is already done only recycles stages so
+// the producer can keep feeding the others; it leaves as soon as the producer announces the end.
+__device__ __forceinline__ bool ring_wait_or_quit(TileRing &r, const int lane, const int stage, const uint32_t phase, const int c)
+{
+    while (true) {
+        int st = 0;
+        if (lane == 0) st = mbar_try_wait(&r.full[stage], phase) ? 1 : (r.limit <= c ? 2 : 0);
+        st = __shfl_sync(0xffffffffu, st, 0);
+        if (st == 1) return true;
+        if (st == 2) return false;
+    }
+}
+
+// Conservative test: can any pixel of the (half-pixel inflated) block [rx0,rx1]x[ry0,ry1] reach
+// alpha >= 1/255 for the splat whose record is at `rp`?  See preprocess.cu cull_footprint.
+__device__ __forceinline__ bool block_may_contribute(const float *rp, const float rx0, const float rx1, const float ry0,
+                                                     const float ry1)
+{
+    const float2 mean = make_float2(rp[9], rp[10]);  // words 9,10 are not 8-byte aligned
+    const float2 e = *reinterpret_cast<const float2 *>(rp + 18);
+    const float4 m = *reinterpret_cast<const float4 *>(rp + 20);  // M00, M01, M11, r2
+    // low-pass disc
+    const float dx = fmaxf(fmaxf(rx0 - mean.x, mean.x - rx1), 0.f);
+    const float dy = fmaxf(fmaxf(ry0 - mean.y, mean.y - ry1), 0.f);
+    if (dx * dx + dy * dy <= m.w) return true;
+    if (m.x == 0.f) return true;  // footprint could not be bounded
+    // ellipse (X-e)^T M (X-e) <= 1: minimum of the convex quadratic over the rectangle
+    const float X0 = rx0 - e.x, X1 = rx1 - e.x, Y0 = ry0 - e.y, Y1 = ry1 - e.y;
+    if (X0 <= 0.f && X1 >= 0.f && Y0 <= 0.f && Y1 >= 0.f) return true;
+    const float ky = -m.y * __frcp_rn(m.z), kx = -m.y * __frcp_rn(m.x);
+    float gmin;
+    {
+        const float Ya = fminf(fmaxf(ky * X0, Y0), Y1), Yb = fminf(fmaxf(ky * X1, Y0), Y1);
+        const float ga = m.x * X0 * X0 + (2.f * m.y * X0 + m.z * Ya) * Ya;
+        const float gb = m.x * X1 * X1 + (2.f * m.y * X1 + m.z * Yb) * Yb;
+        gmin = fminf(ga, gb);
+    }
+    {
+        const float Xa = fminf(fmaxf(kx * Y0, X0), X1), Xb = fminf(fmaxf(kx * Y1, X0), X1);
+        const float ga = m.z * Y0 * Y0 + (2.f * m.y * Y0 + m.x * Xa) * Xa;
+        const float gb = m.z * Y1 * Y1 + (2.f * m.y * Y1 + m.x * Xb) * Xb;
+        gmin = fminf(gmin, fminf(ga, gb));
+    }
+    return gmin <= 1.02f;
+}
+
+}  // namespace surfel

@@ -163,13 +163,13 @@ def debug_binning(width, height, num_rendered, binningBuffer, imageBuffer):
 
 
 def debug_geometry(P, geomBuffer):
-    """(tiles_touched [P], idx_sorted [P], offsets [P], records [P,20]) copied out of the geometry scratch (tests only)."""
+    """(tiles_touched [P], idx_sorted [P], offsets [P], records [P,24]) copied out of the geometry scratch (tests only)."""
     L = _lib.lib()
     dev = geomBuffer.device
     tiles = torch.empty((P,), dtype=torch.int32, device=dev)
     idx = torch.empty((P,), dtype=torch.int32, device=dev)
     offs = torch.empty((P,), dtype=torch.int32, device=dev)
-    recs = torch.empty((P, 20), dtype=torch.float32, device=dev)
+    recs = torch.empty((P, 24), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.surfel_debug_copy_geometry(P, _ptr(geomBuffer), _ptr(tiles), _ptr(idx), _ptr(offs), _ptr(recs),
                                                 _stream()), "surfel_debug_copy_geometry")
