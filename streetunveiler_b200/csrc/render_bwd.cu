@@ -19,6 +19,13 @@
 
 namespace surfel {
 
+__device__ __forceinline__ float fast_rcp(const float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 constexpr int NV = 18;  // gradient values per instance
 
 // Multi-value warp reduction: N values per lane in, one fully reduced value per lane out.
@@ -126,6 +133,12 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
 
     const int my_slot = Butterfly<NV, 4>::slot(lane, 0, NV);
 
+    // Depth / normal / median-depth / distortion upstream gradients are exactly zero for whole frames in
+    // practice (train.py enables those losses late): skip their recurrences when no pixel of the warp has any.
+    const bool aux_any = __any_sync(0xffffffffu, dL_ddepth != 0.f || dL_dreg != 0.f || dL_dmedian_depth != 0.f ||
+                                                     dL_dnormal2D[0] != 0.f || dL_dnormal2D[1] != 0.f ||
+                                                     dL_dnormal2D[2] != 0.f);
+
     int stage = 0;
     uint32_t phase = 0;
     for (int cb = 0; cb < nchunks; cb++) {
@@ -194,10 +207,12 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                                 // The reference keeps (last_alpha, last_color, ...) and folds them into the
                                 // suffix accumulators at the NEXT contributor (backward.cu:329,365-374); folding
                                 // them right after use is the same arithmetic on the same operands, with 8 fewer
-                                // live registers.
-                                T = T / (1.f - alpha);
-                                const float w = alpha * T;
+                                // live registers.  Divisions that only feed gradients (not the alpha / skip
+                                // decisions above) use the approximate reciprocal: <= 2 ulp, far inside the
+                                // 1e-4 tolerance and below the reference's own atomic-order noise.
                                 const float one_m_alpha = 1.f - alpha;
+                                T = T / one_m_alpha;
+                                const float w = alpha * T;
                                 float dL_dalpha = 0.0f;
 #pragma unroll
                                 for (int ch = 0; ch < 3; ch++) {
@@ -207,37 +222,38 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                                     v[12 + ch] = w * dL_dpixel[ch];
                                 }
                                 float dL_dz = 0.0f;
-                                float dL_dweight = 0;
-                                const float m_d = FAR_N / (FAR_N - NEAR_N) * (1 - NEAR_N / c_d);
-                                const float dmd_dd = (FAR_N * NEAR_N) / ((FAR_N - NEAR_N) * c_d * c_d);
-                                if (contributor == median_match) dL_dz += dL_dmedian_depth;
-                                dL_dweight += (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
-                                dL_dalpha += dL_dweight - last_dL_dT;
-                                last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
-                                const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
-                                dL_dz += dL_dmd * dmd_dd;
-
-                                dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-                                accum_depth_rec = alpha * c_d + one_m_alpha * accum_depth_rec;
-                                dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
-                                accum_alpha_rec = alpha * 1.0 + one_m_alpha * accum_alpha_rec;
+                                if (aux_any) {  // warp-uniform: some pixel of this warp has depth/normal/distortion gradients
+                                    const float inv_cd = fast_rcp(c_d);
+                                    const float m_d = FAR_N / (FAR_N - NEAR_N) * (1 - NEAR_N * inv_cd);
+                                    const float dmd_dd = (FAR_N * NEAR_N / (FAR_N - NEAR_N)) * inv_cd * inv_cd;
+                                    if (contributor == median_match) dL_dz += dL_dmedian_depth;
+                                    const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_dreg;
+                                    dL_dalpha += dL_dweight - last_dL_dT;
+                                    last_dL_dT = dL_dweight * alpha + one_m_alpha * last_dL_dT;
+                                    const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
+                                    dL_dz += dL_dmd * dmd_dd;
+                                    dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+                                    accum_depth_rec = alpha * c_d + one_m_alpha * accum_depth_rec;
 #pragma unroll
-                                for (int ch = 0; ch < 3; ch++) {
-                                    dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
-                                    accum_normal_rec[ch] = alpha * normal[ch] + one_m_alpha * accum_normal_rec[ch];
-                                    v[15 + ch] = alpha * T * dL_dnormal2D[ch];
+                                    for (int ch = 0; ch < 3; ch++) {
+                                        dL_dalpha += (normal[ch] - accum_normal_rec[ch]) * dL_dnormal2D[ch];
+                                        accum_normal_rec[ch] = alpha * normal[ch] + one_m_alpha * accum_normal_rec[ch];
+                                        v[15 + ch] = w * dL_dnormal2D[ch];
+                                    }
+                                    dL_dz += w * dL_ddepth;
                                 }
+                                dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
+                                accum_alpha_rec = alpha + one_m_alpha * accum_alpha_rec;
                                 dL_dalpha *= T;
-                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                                dL_dalpha += (-T_final * fast_rcp(one_m_alpha)) * bg_dot_dpixel;
 
                                 const float dL_dG = opa * dL_dalpha;
-                                dL_dz += alpha * T * dL_ddepth;
 
                                 if (rho3d <= rho2d) {
-                                    const float2 dL_ds = make_float2(dL_dG * -G * s.x + dL_dz * Tw.x,
-                                                                     dL_dG * -G * s.y + dL_dz * Tw.y);
-                                    const float dsx_pz = dL_ds.x / p.z;
-                                    const float dsy_pz = dL_ds.y / p.z;
+                                    const float inv_pz = fast_rcp(p.z);
+                                    const float nG = -G * dL_dG;
+                                    const float dsx_pz = (nG * s.x + dL_dz * Tw.x) * inv_pz;
+                                    const float dsy_pz = (nG * s.y + dL_dz * Tw.y) * inv_pz;
                                     const float3 dL_dp = make_float3(dsx_pz, dsy_pz, -(dsx_pz * s.x + dsy_pz * s.y));
                                     const float3 dL_dk = make_float3(l.y * dL_dp.z - l.z * dL_dp.y, l.z * dL_dp.x - l.x * dL_dp.z,
                                                                      l.x * dL_dp.y - l.y * dL_dp.x);
@@ -247,12 +263,11 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                                     v[3] = -dL_dl.x; v[4] = -dL_dl.y; v[5] = -dL_dl.z;
                                     v[6] = pixf.x * dL_dk.x + pixf.y * dL_dl.x + dL_dz * s.x;
                                     v[7] = pixf.x * dL_dk.y + pixf.y * dL_dl.y + dL_dz * s.y;
-                                    v[8] = pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz * 1.0f;
+                                    v[8] = pixf.x * dL_dk.z + pixf.y * dL_dl.z + dL_dz;
                                 } else {
-                                    const float dG_ddelx = -G * FILTER_INV_SQUARE * d.x;
-                                    const float dG_ddely = -G * FILTER_INV_SQUARE * d.y;
-                                    v[9] = dL_dG * dG_ddelx;
-                                    v[10] = dL_dG * dG_ddely;
+                                    const float nG2 = -G * FILTER_INV_SQUARE * dL_dG;
+                                    v[9] = nG2 * d.x;
+                                    v[10] = nG2 * d.y;
                                     v[6] = s.x * dL_dz;
                                     v[7] = s.y * dL_dz;
                                     v[8] = dL_dz;

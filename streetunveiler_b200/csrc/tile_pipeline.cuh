@@ -69,21 +69,62 @@ __device__ __forceinline__ void ring_produce(TileRing &r, const int lane, const 
                                              const float *__restrict__ rec, PosFn position)
 {
     const int nchunks = (total + CHUNK - 1) / CHUNK;
+    constexpr int PER_LANE = CHUNK / 32;
     int stage = 0;
     uint32_t ephase = 1;  // parity of the *previous* phase of `empty`: passes immediately on the first lap
     int issued = 0;
-    for (int c = 0; c < nchunks; c++) {
+    // First lap: every stage is free, so fetch the ids of all NSTAGE chunks with one batch of
+    // independent loads (one exposed memory latency instead of NSTAGE of them) and fire the copies.
+    {
+        uint32_t ids[NSTAGE * PER_LANE];
+        const int first_n = min(total, NSTAGE * CHUNK);
+#pragma unroll
+        for (int q = 0; q < NSTAGE * PER_LANE; q++) {
+            const int slot = (q / PER_LANE) * CHUNK + (q % PER_LANE) * 32 + lane;
+            ids[q] = (slot < first_n) ? point_list[position(slot)] : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < NSTAGE; c++) {
+            if (c < nchunks) {
+                const int n = min(CHUNK, total - c * CHUNK);
+#pragma unroll
+                for (int k = 0; k < PER_LANE; k++) {
+                    const int s = k * 32 + lane;
+                    if (s < n) {
+                        const uint32_t g = ids[c * PER_LANE + k];
+                        if (STORE_IDS) r.id[c][s] = g;
+                        bulk_g2s(&r.rec[c][s * REC_FLOATS], rec + (size_t)g * REC_FLOATS, REC_BYTES, &r.full[c]);
+                    }
+                }
+                if (lane == 0)
+                    mbar_arrive_expect_tx(&r.full[c], (uint32_t)n * REC_BYTES);
+                else
+                    mbar_arrive(&r.full[c]);
+                issued = c + 1;
+            }
+        }
+    }
+    ephase = 0;
+    // Steady state: the ids of chunk c are fetched BEFORE waiting for its stage to drain, so their
+    // latency hides behind the wait.
+    for (int c = NSTAGE; c < nchunks; c++) {
         int stop = (lane == 0 && r.done_warps >= CONSUMER_WARPS) ? 1 : 0;
         stop = __shfl_sync(0xffffffffu, stop, 0);
         if (stop) break;
-        mbar_wait(&r.empty[stage], ephase);
         const int n = min(CHUNK, total - c * CHUNK);
+        uint32_t ids[PER_LANE];
 #pragma unroll
-        for (int s = lane; s < CHUNK; s += 32) {
+        for (int k = 0; k < PER_LANE; k++) {
+            const int s = k * 32 + lane;
+            ids[k] = (s < n) ? point_list[position(c * CHUNK + s)] : 0u;
+        }
+        mbar_wait(&r.empty[stage], ephase);
+#pragma unroll
+        for (int k = 0; k < PER_LANE; k++) {
+            const int s = k * 32 + lane;
             if (s < n) {
-                const uint32_t g = point_list[position(c * CHUNK + s)];
-                if (STORE_IDS) r.id[stage][s] = g;
-                bulk_g2s(&r.rec[stage][s * REC_FLOATS], rec + (size_t)g * REC_FLOATS, REC_BYTES, &r.full[stage]);
+                if (STORE_IDS) r.id[stage][s] = ids[k];
+                bulk_g2s(&r.rec[stage][s * REC_FLOATS], rec + (size_t)ids[k] * REC_FLOATS, REC_BYTES, &r.full[stage]);
             }
         }
         if (lane == 0)
