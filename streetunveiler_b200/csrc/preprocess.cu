@@ -515,22 +515,48 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
     }
 
     // ---- SH VJP (backward.cu:20-139); also writes the zero rows of culled Gaussians ----
+    // The SH row of a Gaussian (12 M bytes) is read and its gradient row written with 128-bit
+    // accesses whenever rows are 16-byte aligned (M % 4 == 0, e.g. the M = 16 of degree 3).
     if (have_sh) {
         float *dsh = dL_dsh + (size_t)idx * M * 3;
+        const float *sh = shs + (size_t)idx * M * 3;
+        const bool vec_ok = ((M & 3) == 0) && M <= 16 && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(shs) & 15) == 0);
         if (!visible) {
-            for (int i = 0; i < 3 * M; i++) dsh[i] = 0.f;
+            if (vec_ok) {
+                float4 *d4 = reinterpret_cast<float4 *>(dsh);
+                for (int i = 0; i < (3 * M) / 4; i++) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int i = 0; i < 3 * M; i++) dsh[i] = 0.f;
+            }
         } else {
             const float len = sqrtf(dot3(dirx, diry, dirz, dirx, diry, dirz));
             const float x = dirx / len, y = diry / len, z = dirz / len;
-            const float *sh = shs + (size_t)idx * M * 3;
+            const int ncoef = (D + 1) * (D + 1);
+            float shl[48], dl[48];
+#pragma unroll
+            for (int i = 0; i < 48; i++) dl[i] = 0.f;
+            if (vec_ok) {
+                const float4 *s4 = reinterpret_cast<const float4 *>(sh);
+#pragma unroll
+                for (int i = 0; i < 12; i++)
+                    if (i * 4 < ncoef * 3) {
+                        const float4 t = __ldg(s4 + i);
+                        shl[4 * i] = t.x; shl[4 * i + 1] = t.y; shl[4 * i + 2] = t.z; shl[4 * i + 3] = t.w;
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 48; i++)
+                    if (i < ncoef * 3) shl[i] = __ldg(sh + i);
+            }
             float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
-#define SH(k, c) __ldg(sh + 3 * (k) + (c))
-#define DSH(k, v)                                             \
-    {                                                         \
-        const float vv = (v);                                 \
-        dsh[3 * (k)] = vv * dRGB[0];                          \
-        dsh[3 * (k) + 1] = vv * dRGB[1];                      \
-        dsh[3 * (k) + 2] = vv * dRGB[2];                      \
+#define SH(k, c) shl[3 * (k) + (c)]
+#define DSH(k, v)                                            \
+    {                                                        \
+        const float vv = (v);                                \
+        dl[3 * (k)] = vv * dRGB[0];                          \
+        dl[3 * (k) + 1] = vv * dRGB[1];                      \
+        dl[3 * (k) + 2] = vv * dRGB[2];                      \
     }
             DSH(0, kSH_C0);
             if (D > 0) {
@@ -583,10 +609,19 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
                     }
                 }
             }
-            // coefficients above the active degree receive exact zeros
-            for (int k = (D + 1) * (D + 1); k < M; k++) DSH(k, 0.f);
 #undef SH
 #undef DSH
+            // coefficients above the active degree keep their exact zeros
+            if (vec_ok) {
+                float4 *d4 = reinterpret_cast<float4 *>(dsh);
+#pragma unroll
+                for (int i = 0; i < 12; i++)
+                    if (i * 4 < 3 * M) d4[i] = make_float4(dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 48; i++)
+                    if (i < 3 * M) dsh[i] = dl[i];
+            }
             const float ddx = dot3(dRGBdx[0], dRGBdx[1], dRGBdx[2], dRGB[0], dRGB[1], dRGB[2]);
             const float ddy = dot3(dRGBdy[0], dRGBdy[1], dRGBdy[2], dRGB[0], dRGB[1], dRGB[2]);
             const float ddz = dot3(dRGBdz[0], dRGBdz[1], dRGBdz[2], dRGB[0], dRGB[1], dRGB[2]);

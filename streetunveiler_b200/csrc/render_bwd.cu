@@ -19,6 +19,13 @@
 
 namespace surfel {
 
+// Fire-and-forget float reduction (RED, no return value): unlike ATOMG it does not hold a scoreboard
+// until the L2 round trip completes, so the warp moves on to the next instance immediately.
+__device__ __forceinline__ void red_add_f32(float *addr, const float v)
+{
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float fast_rcp(const float x)
 {
     float r;
@@ -279,7 +286,7 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
                 }
                 if (__any_sync(0xffffffffu, valid)) {
                     Butterfly<NV, 4>::run(v, lane);
-                    if (my_slot >= 0) atomicAdd(gacc + (size_t)ring.id[stage][jj] * GACC_FLOATS + my_slot, v[0]);
+                    if (my_slot >= 0) red_add_f32(gacc + (size_t)ring.id[stage][jj] * GACC_FLOATS + my_slot, v[0]);
                 }
             }
         }
