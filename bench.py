@@ -130,12 +130,12 @@ def alg_bytes_stage(stage, P, P_vis, R, HW, K=16):
     IN = 12 + 8 + 16 + 4 + 12 * K
     OUT = 12 + 12 + 4 + 8 + 16 + 12 * K
     return {
-        "preprocess_fwd": P * (40 + 4 + 4 + 4 + 4) + P_vis * (12 * K + 80 + 1),   # params in; radii/tiles/key/iota out; SH in + record out
+        "preprocess_fwd": P * (40 + 4 + 4 + 4 + 4) + P_vis * (12 * K + 96 + 1),   # params in; radii/tiles/key/iota out; SH in + record out
         "depth_order": P * 8 * 2 * 4 + P * 12,                                    # 4 digit passes of 8 B pairs (r+w) + scan
         "tile_binning": P * 12 + R * 8 + R * 16 * 2 + R * 4,                      # emit 8 B/inst, 2 digit passes r+w, ranges read
-        "render_fwd": R * 4 + P_vis * 80 + HW * 60,                               # ids + each record once + 15 planes out
-        "render_bwd": R * 4 + P_vis * (80 + 72) + HW * 60,                        # ids + records + grad record out + 15 planes in
-        "preprocess_bwd": P * 4 + P_vis * (IN + 80 + 72) + P * OUT,               # radii; params+record+grad record in; grads out
+        "render_fwd": R * 4 + P_vis * 96 + HW * 60,                               # ids + each record once + 15 planes out
+        "render_bwd": R * 4 + P_vis * (96 + 72) + HW * 60,                        # ids + records + grad record out + 15 planes in
+        "preprocess_bwd": P * 4 + P_vis * (IN + 96 + 72) + P * OUT,               # radii; params+record+grad record in; grads out
     }[stage]
 
 
