@@ -8,9 +8,10 @@ A "step" is one forward + one backward of the rasterizer operator over one synth
 
   * N = 1 (default): BASELINE config 3 -- STREET(P=2,000,000, seed 1), CAM-A 1920x1280, SH degree 3,
     colour + alpha upstream gradients.
-  * N > 1 (torchrun, one rank per GPU): weak scaling -- every rank owns a depth slab of 2,000,000
-    surfels of one STREET(2,000,000*N) scene and the ranks composite their slabs into one image
-    (streetunveiler_b200/sharded.py).
+  * N > 1 (torchrun, one rank per GPU): weak scaling -- every rank owns 2,000,000 surfels (an index
+    shard) of one STREET(2,000,000*N) scene; projected records are all-gathered, every rank blends
+    its interleaved tile rows, images are all-reduced and gradient records reduce-scattered to the
+    owners (streetunveiler_b200/sharded.py).
   * --impl reference: the UNMODIFIED reference CUDA extension rebuilt for sm_100a (oracle/_ref), same
     inputs and timing protocol, on the same GPU; falls back to the CPU oracle port when that build
     is absent.  --impl reference-cpu forces the CPU oracle port (host cores).
@@ -146,11 +147,9 @@ class Workload:
     def __init__(self, P_total, seed, world, rank, device):
         self.cam = syn.cam_a()
         scene = syn.street_scene(P_total, seed, 3)
-        if world > 1:
-            order = syn.depth_separable_order(scene["means3D"], self.cam)
+        if world > 1:  # shard by Gaussian index: rank r owns rows [r P/G, (r+1) P/G)
             lo, hi = rank * (P_total // world), (rank + 1) * (P_total // world)
-            sel = order[lo:hi]
-            scene = {k: (v[sel].contiguous() if isinstance(v, torch.Tensor) else v) for k, v in scene.items()}
+            scene = {k: (v[lo:hi].contiguous() if isinstance(v, torch.Tensor) else v) for k, v in scene.items()}
         self.host = scene
         self.crc = syn.scene_crc(scene)
         self.P = scene["means3D"].shape[0]
@@ -316,7 +315,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"STREET(P={P_total}, seed={1 if world == 1 else 2}) CAM-A 1920x1280 SH3, "
                                f"grads colour+alpha; BASELINE configs[2]" + ("" if world == 1 else
-                               f"; depth-slab shards of {P_PER_GPU} surfels per GPU, composited over NCCL"),
+                               f"; index shards of {P_PER_GPU} surfels per GPU, record all-gather + tile-row windows + image all-reduce + gradient reduce-scatter over NCCL"),
                    "P_total": P_total, "P_per_gpu": wl.P, "num_rendered": R, "visible": P_vis, "input_crc32": wl.crc,
                    "l2": "inputs (464 MB/GPU) larger than the 126 MB L2; no explicit flush"},
         "clocks": clocks,

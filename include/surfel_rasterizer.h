@@ -147,6 +147,53 @@ SURFEL_API int surfel_debug_copy_binning(int width, int height, int64_t num_rend
                               const char *binning_buffer, const char *image_buffer,
                               uint32_t *ranges_out, uint32_t *point_list_out, void *stream);
 
+/*
+ * ---------------------------------------------------------------------------------------------
+ * Sharded (multi-GPU) path -- not part of the reference, which is single-GPU only.
+ * Gaussians are sharded by index across ranks; the screen is partitioned by tile rows
+ * ("window": rows y with y >= row_offset and (y - row_offset) % row_stride == 0).  Call sequence
+ * per rank (host side: streetunveiler_b200/sharded.py):
+ *   surfel_shard_preprocess   own shard -> projected records [P,24] fp32, radii, depth keys, clamp bytes
+ *   (all-gather of records / radii / depth keys over NCCL)
+ *   surfel_window_prepare     depth order of ALL gathered Gaussians, instance count of the own window
+ *   surfel_window_render      binning + blend of the own tile rows into full-size image planes
+ *   (all-gather of the image rows)
+ *   surfel_window_backward    gradient records [P_total,20] of the own tile rows (zeroed by the call)
+ *   (reduce-scatter of the gradient records to the owners of the Gaussians)
+ *   surfel_shard_backward     own shard: gradient record -> parameter gradients
+ * Every per-pixel result is identical to the single-GPU path (same lists, same order).
+ * ---------------------------------------------------------------------------------------------
+ */
+SURFEL_API int surfel_shard_preprocess(
+    int P, int D, int M, int width, int height,
+    const float *means3D, const float *shs, const float *colors_precomp, const float *opacities,
+    const float *scales, float scale_modifier, const float *rotations, const float *transMat_precomp,
+    const float *viewmatrix, const float *projmatrix, const float *cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    int *radii, float *records, uint32_t *depth_keys, unsigned char *clamped, void *stream);
+SURFEL_API size_t surfel_window_bytes(int P_total);
+SURFEL_API int surfel_window_prepare(
+    int P_total, int width, int height, int row_offset, int row_stride,
+    const float *records, const int *radii, const uint32_t *depth_keys,
+    char *window_buffer, int64_t *num_rendered, void *stream, int debug);
+SURFEL_API int surfel_window_render(
+    int P_total, int width, int height, int row_offset, int row_stride, int64_t num_rendered,
+    const float *background, const float *records, const int *radii,
+    char *window_buffer, char *binning_buffer, char *image_buffer,
+    float *out_color, float *out_others, void *stream, int debug);
+SURFEL_API int surfel_window_backward(
+    int P_total, int width, int height, int row_offset, int row_stride, int64_t num_rendered,
+    const float *background, const float *records, char *binning_buffer, char *image_buffer,
+    const float *dL_dpix, const float *dL_dothers, float *grad_records, void *stream, int debug);
+SURFEL_API int surfel_shard_backward(
+    int P, int D, int M, int width, int height,
+    const float *means3D, const float *shs, const float *scales, const float *rotations,
+    const float *transMat_precomp, const float *viewmatrix, const float *projmatrix, const float *cam_pos,
+    float tan_fovx, float tan_fovy,
+    const int *radii, const float *records, const unsigned char *clamped, const float *grad_records,
+    float *dL_dmean2D, float *dL_dnormal, float *dL_dopacity, float *dL_dcolor,
+    float *dL_dmean3D, float *dL_dtransMat, float *dL_dsh, float *dL_dscale, float *dL_drot, void *stream);
+
 /* Debug view of the geometry scratch: per-Gaussian tile counts [P], depth-ordered ids [P], inclusive
  * offsets [P] (all uint32) and the packed 96-byte projected records [P,24] (fp32 words). Any output
  * may be NULL. */

@@ -130,6 +130,27 @@ BinView carve_bin(char *base, int64_t R, size_t cub_bytes)
     return b;
 }
 
+// Scratch of the sharded path's per-rank window pass (P = all gathered Gaussians).
+struct WindowView {
+    uint32_t *tiles_touched, *idx_in, *idx_sorted, *depth_key_sorted, *offsets;
+    char *cub_temp;
+    size_t cub_temp_bytes;
+};
+WindowView carve_window(char *base, int P, size_t cub_bytes)
+{
+    WindowView w;
+    char *p = base;
+    const size_t n = (size_t)(P > 0 ? P : 1);
+    w.tiles_touched = carve<uint32_t>(p, n);
+    w.idx_in = carve<uint32_t>(p, n);
+    w.idx_sorted = carve<uint32_t>(p, n);
+    w.depth_key_sorted = carve<uint32_t>(p, n);
+    w.offsets = carve<uint32_t>(p, n);
+    w.cub_temp = carve<char>(p, cub_bytes);
+    w.cub_temp_bytes = cub_bytes;
+    return w;
+}
+
 bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 bool have_device()
@@ -278,7 +299,7 @@ int surfel_forward_render(int P, int width, int height, int64_t num_rendered, co
         bv = carve_bin(binning_buffer, num_rendered, cub);
     }
     StageClock clk_bin(st, 2);
-    CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, g.rec, radii, g.idx_sorted, g.offsets,
+    CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, 0, 1, g.rec, radii, g.idx_sorted, g.offsets,
                                         bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted, bv.point_list, iv.ranges,
                                         bv.cub_temp, bv.cub_temp_bytes, st));
     clk_bin.stop();
@@ -392,6 +413,170 @@ int surfel_debug_copy_binning(int width, int height, int64_t num_rendered, const
         CK("copy point list", cudaMemcpyAsync(point_list_out, bv.point_list, (size_t)num_rendered * sizeof(uint32_t),
                                               cudaMemcpyDeviceToDevice, st));
     }
+    return 0;
+}
+
+// =====================================================================================================
+// Sharded path (DESIGN.md "Multi-GPU"): Gaussians sharded by index, screen partitioned by tile rows.
+// =====================================================================================================
+int surfel_shard_preprocess(int P, int D, int M, int width, int height, const float *means3D, const float *shs,
+                            const float *colors_precomp, const float *opacities, const float *scales,
+                            float scale_modifier, const float *rotations, const float *transMat_precomp,
+                            const float *viewmatrix, const float *projmatrix, const float *cam_pos, float tan_fovx,
+                            float tan_fovy, int prefiltered, int *radii, float *records, uint32_t *depth_keys,
+                            unsigned char *clamped, void *stream)
+{
+    (void)tan_fovx; (void)tan_fovy;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0) return fail("surfel_shard_preprocess", "bad sizes");
+    if (P == 0) return 0;
+    if (!means3D || !opacities || !viewmatrix || !projmatrix || !cam_pos || !radii || !records || !depth_keys || !clamped)
+        return fail("surfel_shard_preprocess", "NULL required pointer");
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+        return fail("surfel_shard_preprocess", "provide exactly one of shs / colors_precomp");
+    const bool have_sr = scales != nullptr && rotations != nullptr;
+    if (have_sr == (transMat_precomp != nullptr))
+        return fail("surfel_shard_preprocess", "provide exactly one of (scales, rotations) / transMat_precomp");
+    if (!aligned(records, 16) || (have_sr && (!aligned(scales, 8) || !aligned(rotations, 16))))
+        return fail("surfel_shard_preprocess", "alignment");
+    PreprocessFwdArgs a;
+    a.P = P; a.D = D; a.M = M; a.W = width; a.H = height;
+    a.gx = (width + TILE_X - 1) / TILE_X; a.gy = (height + TILE_Y - 1) / TILE_Y;
+    a.prefiltered = prefiltered; a.scale_modifier = scale_modifier;
+    a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.opacities = opacities; a.shs = shs;
+    a.transMat_precomp = transMat_precomp; a.colors_precomp = colors_precomp;
+    a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+    a.radii = radii; a.rec = records; a.tiles_touched = nullptr; a.depth_key = depth_keys; a.idx_in = nullptr;
+    a.clamped = clamped;
+    launch_preprocess_fwd(a, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda("surfel_shard_preprocess", e);
+    return 0;
+}
+
+size_t surfel_window_bytes(int P_total)
+{
+    if (P_total < 0) { fail("surfel_window_bytes", "negative P"); return 0; }
+    if (!have_device()) { fail("surfel_window_bytes", "no CUDA device (this library has no CPU path)"); return 0; }
+    const size_t cub = depth_sort_temp_bytes(P_total);
+    WindowView w = carve_window(nullptr, P_total, cub);
+    return (size_t)(w.cub_temp + cub) + 128;
+}
+
+int surfel_window_prepare(int P_total, int width, int height, int row_offset, int row_stride, const float *records,
+                          const int *radii, const uint32_t *depth_keys, char *window_buffer, int64_t *num_rendered,
+                          void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!num_rendered) return fail("surfel_window_prepare", "num_rendered is NULL");
+    *num_rendered = 0;
+    if (P_total < 0 || width <= 0 || height <= 0 || row_offset < 0 || row_stride < 1)
+        return fail("surfel_window_prepare", "bad sizes");
+    if (P_total == 0) return 0;
+    if (!records || !radii || !depth_keys || !window_buffer) return fail("surfel_window_prepare", "NULL required pointer");
+    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    WindowView w = carve_window(window_buffer, P_total, depth_sort_temp_bytes(P_total));
+    launch_count_window_tiles(P_total, gx, gy, row_offset, row_stride, records, radii, w.tiles_touched, w.idx_in, st);
+    STAGE("window tile count");
+    CK("depth order", run_depth_order(P_total, depth_keys, w.depth_key_sorted, w.idx_in, w.idx_sorted, w.tiles_touched,
+                                      w.offsets, nullptr, w.cub_temp, w.cub_temp_bytes, st));
+    STAGE("depth order");
+    uint32_t r32 = 0;
+    CK("num_rendered readback", cudaMemcpyAsync(&r32, w.offsets + (P_total - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK("num_rendered readback", cudaStreamSynchronize(st));
+    *num_rendered = (int64_t)r32;
+    return 0;
+}
+
+int surfel_window_render(int P_total, int width, int height, int row_offset, int row_stride, int64_t num_rendered,
+                         const float *background, const float *records, const int *radii, char *window_buffer,
+                         char *binning_buffer, char *image_buffer, float *out_color, float *out_others, void *stream,
+                         int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P_total < 0 || width <= 0 || height <= 0 || num_rendered < 0 || row_offset < 0 || row_stride < 1)
+        return fail("surfel_window_render", "bad sizes");
+    if (!background || !image_buffer || !out_color || !out_others) return fail("surfel_window_render", "NULL required pointer");
+    if (P_total > 0 && (!records || !radii || !window_buffer)) return fail("surfel_window_render", "NULL geometry");
+    if (num_rendered > 0 && !binning_buffer) return fail("surfel_window_render", "NULL binning_buffer");
+    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    ImageView iv = carve_image(image_buffer, width, height);
+    WindowView w{};
+    BinView bv{};
+    if (P_total > 0) w = carve_window(window_buffer, P_total, depth_sort_temp_bytes(P_total));
+    if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
+    CK("tile binning", run_tile_binning(P_total, num_rendered, gx, gy, row_offset, row_stride, records, radii,
+                                        w.idx_sorted, w.offsets, bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted,
+                                        bv.point_list, iv.ranges, bv.cub_temp, bv.cub_temp_bytes, st));
+    STAGE("tile binning");
+    RenderFwdArgs r;
+    r.W = width; r.H = height; r.gx = gx; r.gy = gy; r.row_offset = row_offset; r.row_stride = row_stride;
+    r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = records; r.bg = background;
+    r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
+    r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
+    launch_render_fwd(r, st);
+    STAGE("render forward");
+    return 0;
+}
+
+int surfel_window_backward(int P_total, int width, int height, int row_offset, int row_stride, int64_t num_rendered,
+                           const float *background, const float *records, char *binning_buffer, char *image_buffer,
+                           const float *dL_dpix, const float *dL_dothers, float *grad_records, void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P_total < 0 || width <= 0 || height <= 0 || num_rendered < 0 || row_offset < 0 || row_stride < 1)
+        return fail("surfel_window_backward", "bad sizes");
+    if (P_total == 0) return 0;
+    if (!background || !records || !image_buffer || !dL_dpix || !dL_dothers || !grad_records)
+        return fail("surfel_window_backward", "NULL required pointer");
+    if (!aligned(grad_records, 16)) return fail("surfel_window_backward", "grad_records must be 16-byte aligned");
+    CK("grad records clear", cudaMemsetAsync(grad_records, 0, (size_t)P_total * GACC_FLOATS * sizeof(float), st));
+    if (num_rendered == 0) return 0;
+    if (!binning_buffer) return fail("surfel_window_backward", "NULL binning_buffer");
+    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    ImageView iv = carve_image(image_buffer, width, height);
+    BinView bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
+    RenderBwdArgs r;
+    r.W = width; r.H = height; r.gx = gx; r.gy = gy; r.row_offset = row_offset; r.row_stride = row_stride;
+    r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = records; r.bg = background;
+    r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
+    r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = grad_records; r.subtile_cull = g_subtile_cull;
+    launch_render_bwd(r, st);
+    STAGE("render backward");
+    return 0;
+}
+
+int surfel_shard_backward(int P, int D, int M, int width, int height, const float *means3D, const float *shs,
+                          const float *scales, const float *rotations, const float *transMat_precomp,
+                          const float *viewmatrix, const float *projmatrix, const float *cam_pos, float tan_fovx,
+                          float tan_fovy, const int *radii, const float *records, const unsigned char *clamped,
+                          const float *grad_records, float *dL_dmean2D, float *dL_dnormal, float *dL_dopacity,
+                          float *dL_dcolor, float *dL_dmean3D, float *dL_dtransMat, float *dL_dsh, float *dL_dscale,
+                          float *dL_drot, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0) return fail("surfel_shard_backward", "bad sizes");
+    if (P == 0) return 0;
+    if (!means3D || !viewmatrix || !projmatrix || !cam_pos || !radii || !records || !clamped || !grad_records ||
+        !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dtransMat || !dL_dscale || !dL_drot)
+        return fail("surfel_shard_backward", "NULL required pointer");
+    if (shs && M > 0 && !dL_dsh) return fail("surfel_shard_backward", "dL_dsh is NULL but shs given");
+    if (!aligned(grad_records, 16) || !aligned(dL_dscale, 8) || !aligned(dL_drot, 16))
+        return fail("surfel_shard_backward", "alignment");
+    PreprocessBwdArgs a;
+    a.P = P; a.D = D; a.M = M;
+    a.focal_y = height / (2.0f * tan_fovy);
+    a.focal_x = width / (2.0f * tan_fovx);
+    a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+    a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
+    a.transMat_precomp = transMat_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+    a.radii = radii; a.clamped = clamped; a.rec = records; a.gacc = grad_records;
+    a.dL_dmean2D = dL_dmean2D; a.dL_dnormal = dL_dnormal; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
+    a.dL_dmean3D = dL_dmean3D; a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale;
+    a.dL_drot = dL_drot;
+    launch_preprocess_bwd(a, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda("surfel_shard_backward", e);
     return 0;
 }
 

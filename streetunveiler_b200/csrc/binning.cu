@@ -58,12 +58,21 @@ cudaError_t run_depth_order(int P, const uint32_t *depth_key, uint32_t *depth_ke
     return cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, offsets, P, stream);
 }
 
+// A tile-row window {y : y >= row_offset, (y - row_offset) % row_stride == 0} selects the tile rows a
+// rank renders in the sharded path (row_offset = 0, row_stride = 1: the whole screen).
+__device__ __forceinline__ int first_row_in_window(const int y0, const int row_offset, const int row_stride)
+{
+    if (y0 <= row_offset) return row_offset;
+    const int k = (y0 - row_offset + row_stride - 1) / row_stride;
+    return row_offset + k * row_stride;
+}
+
 // One thread per depth-ordered Gaussian: write its (tile id, Gaussian id) instances.
 __global__ void __launch_bounds__(256)
-emit_instances_kernel(const int P, const int gx, const int gy, const float *__restrict__ rec,
-                      const int *__restrict__ radii, const uint32_t *__restrict__ idx_sorted,
-                      const uint32_t *__restrict__ offsets, uint32_t *__restrict__ keys,
-                      uint32_t *__restrict__ vals)
+emit_instances_kernel(const int P, const int gx, const int gy, const int row_offset, const int row_stride,
+                      const float *__restrict__ rec, const int *__restrict__ radii,
+                      const uint32_t *__restrict__ idx_sorted, const uint32_t *__restrict__ offsets,
+                      uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
@@ -78,12 +87,44 @@ emit_instances_kernel(const int P, const int gx, const int gy, const float *__re
     const int y0 = min(gy, max(0, (int)((py - r) / TILE_Y)));
     const int x1 = min(gx, max(0, (int)((px + r + TILE_X - 1) / TILE_X)));
     const int y1 = min(gy, max(0, (int)((py + r + TILE_Y - 1) / TILE_Y)));
-    for (int y = y0; y < y1; y++)
+    for (int y = first_row_in_window(y0, row_offset, row_stride); y < y1; y += row_stride)
         for (int x = x0; x < x1; x++) {
             keys[off] = (uint32_t)(y * gx + x);
             vals[off] = g;
             off++;
         }
+}
+
+// Tiles of each Gaussian's rect that fall into the window (sharded path; the single-GPU path gets the
+// full count from preprocess).
+__global__ void __launch_bounds__(256)
+count_window_tiles_kernel(const int P, const int gx, const int gy, const int row_offset, const int row_stride,
+                          const float *__restrict__ rec, const int *__restrict__ radii,
+                          uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ idx_in)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P) return;
+    idx_in[g] = (uint32_t)g;
+    const int r = radii[g];
+    uint32_t n = 0;
+    if (r > 0) {
+        const float px = rec[(size_t)g * REC_FLOATS + 9], py = rec[(size_t)g * REC_FLOATS + 10];
+        const int x0 = min(gx, max(0, (int)((px - r) / TILE_X)));
+        const int y0 = min(gy, max(0, (int)((py - r) / TILE_Y)));
+        const int x1 = min(gx, max(0, (int)((px + r + TILE_X - 1) / TILE_X)));
+        const int y1 = min(gy, max(0, (int)((py + r + TILE_Y - 1) / TILE_Y)));
+        const int yf = first_row_in_window(y0, row_offset, row_stride);
+        if (yf < y1) n = (uint32_t)(((y1 - 1 - yf) / row_stride + 1) * (x1 - x0));
+    }
+    tiles_touched[g] = n;
+}
+
+void launch_count_window_tiles(int P, int gx, int gy, int row_offset, int row_stride, const float *rec,
+                               const int *radii, uint32_t *tiles_touched, uint32_t *idx_in, cudaStream_t stream)
+{
+    if (P == 0) return;
+    count_window_tiles_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, gy, row_offset, row_stride, rec, radii,
+                                                                   tiles_touched, idx_in);
 }
 
 __global__ void __launch_bounds__(256)
@@ -104,15 +145,16 @@ tile_ranges_kernel(const int64_t R, const uint32_t *__restrict__ keys_sorted, ui
     if (i == R - 1) ranges[cur].y = (uint32_t)R;
 }
 
-cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, const float *rec, const int *radii,
+cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, int row_stride, const float *rec,
+                             const int *radii,
                              const uint32_t *idx_sorted, const uint32_t *offsets, uint32_t *keys_unsorted,
                              uint32_t *vals_unsorted, uint32_t *keys_sorted, uint32_t *point_list, uint2 *ranges,
                              char *temp, size_t temp_bytes, cudaStream_t stream)
 {
     cudaError_t e = cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream);
     if (e != cudaSuccess || R == 0 || P == 0) return e;
-    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, gy, rec, radii, idx_sorted, offsets,
-                                                               keys_unsorted, vals_unsorted);
+    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, gy, row_offset, row_stride, rec, radii,
+                                                               idx_sorted, offsets, keys_unsorted, vals_unsorted);
     int bits = 1;
     while ((1u << bits) < (uint32_t)(gx * gy)) bits++;
     e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_unsorted, keys_sorted, vals_unsorted, point_list, R, 0,

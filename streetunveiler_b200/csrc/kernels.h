@@ -40,7 +40,10 @@ cudaError_t run_depth_order(int P, const uint32_t *depth_key, uint32_t *depth_ke
                             uint32_t *idx_sorted, const uint32_t *tiles_touched, uint32_t *offsets,
                             int64_t *num_rendered_dev, char *temp, size_t temp_bytes, cudaStream_t stream);
 // emit (tile, id) pairs in depth order, stable-sort by tile, find per-tile ranges
-cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, const float *rec, const int *radii,
+void launch_count_window_tiles(int P, int gx, int gy, int row_offset, int row_stride, const float *rec,
+                               const int *radii, uint32_t *tiles_touched, uint32_t *idx_in, cudaStream_t stream);
+cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, int row_stride, const float *rec,
+                             const int *radii,
                              const uint32_t *idx_sorted, const uint32_t *offsets, uint32_t *keys_unsorted,
                              uint32_t *vals_unsorted, uint32_t *keys_sorted, uint32_t *point_list, uint2 *ranges,
                              char *temp, size_t temp_bytes, cudaStream_t stream);
@@ -48,6 +51,7 @@ cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, const float *rec,
 // ---- render (render_fwd.cu / render_bwd.cu) ----
 struct RenderFwdArgs {
     int W, H, gx, gy;
+    int row_offset = 0, row_stride = 1;  // tile-row window rendered by this call
     const uint2 *ranges;
     const uint32_t *point_list;
     const float *rec;
@@ -62,6 +66,7 @@ void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream);
 
 struct RenderBwdArgs {
     int W, H, gx, gy;
+    int row_offset = 0, row_stride = 1;
     const uint2 *ranges;
     const uint32_t *point_list;
     const float *rec;

@@ -307,9 +307,9 @@ preprocess_fwd_kernel(const int P, const int D, const int M, const float *__rest
     } while (false);
 
     radii[idx] = radius_out;
-    tiles_touched[idx] = tiles_out;
+    if (tiles_touched) tiles_touched[idx] = tiles_out;   // NULL in the sharded path (counted per tile-row window later)
     depth_key[idx] = key_out;
-    idx_in[idx] = (uint32_t)idx;
+    if (idx_in) idx_in[idx] = (uint32_t)idx;
 }
 
 void launch_preprocess_fwd(const PreprocessFwdArgs &a, cudaStream_t stream)

@@ -67,7 +67,8 @@ struct Butterfly {
 
 template <bool CULL>
 __global__ void __maxnreg__(96)
-render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restrict__ ranges,
+render_bwd_kernel(const int W, const int H, const int gx, const int row_offset, const int row_stride,
+                  const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
                   const float *__restrict__ bg, const float *__restrict__ final_Ts,
                   const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tile_max_contrib,
@@ -78,7 +79,8 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
+    // blockIdx.x enumerates the tiles of this call's row window
+    const int tile = (row_offset + row_stride * ((int)blockIdx.x / gx)) * gx + (int)blockIdx.x % gx;
     const uint2 range = ranges[tile];
     // only list positions [0, total) can have been blended by some pixel of this tile
     const int total = min((int)(range.y - range.x), (int)tile_max_contrib[tile]);
@@ -298,14 +300,15 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint2 *__restric
 
 void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
 {
-    const int tiles = a.gx * a.gy;
+    const int rows = a.gy > a.row_offset ? (a.gy - a.row_offset + a.row_stride - 1) / a.row_stride : 0;
+    const int tiles = a.gx * rows;
     if (tiles == 0) return;
     if (a.subtile_cull)
-        render_bwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
+        render_bwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.row_offset, a.row_stride, a.ranges, a.point_list, a.rec, a.bg,
                                                            a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
                                                            a.dL_dothers, a.gacc);
     else
-        render_bwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.ranges, a.point_list, a.rec, a.bg,
+        render_bwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.row_offset, a.row_stride, a.ranges, a.point_list, a.rec, a.bg,
                                                             a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
                                                             a.dL_dothers, a.gacc);
 }
