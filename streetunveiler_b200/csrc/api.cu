@@ -113,6 +113,7 @@ ImageView carve_image(char *base, int W, int H)
     v.final_T = carve<float>(p, 3 * HW);
     v.n_contrib = carve<uint32_t>(p, 2 * HW);
     v.tile_max_contrib = carve<uint32_t>(p, tiles);
+    v.tile_order = carve<uint32_t>(p, tiles);
     return v;
 }
 
@@ -203,7 +204,7 @@ size_t surfel_image_bytes(int width, int height)
     if (width <= 0 || height <= 0) { fail("surfel_image_bytes", "bad image size"); return 0; }
     ImageView v = carve_image(nullptr, width, height);
     const size_t tiles = (size_t)((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
-    return (size_t)(v.tile_max_contrib + tiles) + 128;
+    return (size_t)(v.tile_order + tiles) + 128;
 }
 
 size_t surfel_binning_bytes(int64_t num_rendered)
@@ -301,13 +302,13 @@ int surfel_forward_render(int P, int width, int height, int64_t num_rendered, co
     StageClock clk_bin(st, 2);
     CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, 0, 1, g.rec, radii, g.idx_sorted, g.offsets,
                                         bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted, bv.point_list, iv.ranges,
-                                        bv.cub_temp, bv.cub_temp_bytes, st));
+                                        iv.tile_order, bv.cub_temp, bv.cub_temp_bytes, st));
     clk_bin.stop();
     STAGE("tile binning");
 
     RenderFwdArgs r;
     r.W = width; r.H = height; r.gx = gx; r.gy = gy;
-    r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
+    r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
     r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
     r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
     {
@@ -355,7 +356,7 @@ int surfel_backward(int P, int D, int M, int64_t num_rendered, const float *back
     if (num_rendered > 0) {
         RenderBwdArgs r;
         r.W = width; r.H = height; r.gx = gx; r.gy = gy;
-        r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
+        r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
         r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
         r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = gacc; r.subtile_cull = g_subtile_cull;
         {
@@ -507,11 +508,11 @@ int surfel_window_render(int P_total, int width, int height, int row_offset, int
     if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
     CK("tile binning", run_tile_binning(P_total, num_rendered, gx, gy, row_offset, row_stride, records, radii,
                                         w.idx_sorted, w.offsets, bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted,
-                                        bv.point_list, iv.ranges, bv.cub_temp, bv.cub_temp_bytes, st));
+                                        bv.point_list, iv.ranges, iv.tile_order, bv.cub_temp, bv.cub_temp_bytes, st));
     STAGE("tile binning");
     RenderFwdArgs r;
     r.W = width; r.H = height; r.gx = gx; r.gy = gy; r.row_offset = row_offset; r.row_stride = row_stride;
-    r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = records; r.bg = background;
+    r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = records; r.bg = background;
     r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
     r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
     launch_render_fwd(r, st);
@@ -538,7 +539,7 @@ int surfel_window_backward(int P_total, int width, int height, int row_offset, i
     BinView bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
     RenderBwdArgs r;
     r.W = width; r.H = height; r.gx = gx; r.gy = gy; r.row_offset = row_offset; r.row_stride = row_stride;
-    r.ranges = iv.ranges; r.point_list = bv.point_list; r.rec = records; r.bg = background;
+    r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = records; r.bg = background;
     r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
     r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = grad_records; r.subtile_cull = g_subtile_cull;
     launch_render_bwd(r, st);

@@ -145,14 +145,47 @@ tile_ranges_kernel(const int64_t R, const uint32_t *__restrict__ keys_sorted, ui
     if (i == R - 1) ranges[cur].y = (uint32_t)R;
 }
 
+// Launch order of the tiles of a window: longest instance lists first (buckets of floor(log2(len))),
+// so that the few very long lists start at t = 0 instead of forming the tail of the blend kernels.
+__global__ void __launch_bounds__(1024)
+order_tiles_kernel(const int gx, const int rows, const int row_offset, const int row_stride,
+                   const uint2 *__restrict__ ranges, uint32_t *__restrict__ order)
+{
+    __shared__ uint32_t hist[33], base[33];
+    const int n = gx * rows;
+    if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int tile = (row_offset + row_stride * (j / gx)) * gx + j % gx;
+        const uint2 r = ranges[tile];
+        atomicAdd(&hist[32 - __clz(r.y - r.x)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int b = 32; b >= 0; b--) { base[b] = acc; acc += hist[b]; }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int tile = (row_offset + row_stride * (j / gx)) * gx + j % gx;
+        const uint2 r = ranges[tile];
+        order[atomicAdd(&base[32 - __clz(r.y - r.x)], 1u)] = (uint32_t)tile;
+    }
+}
+
 cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, int row_stride, const float *rec,
                              const int *radii,
                              const uint32_t *idx_sorted, const uint32_t *offsets, uint32_t *keys_unsorted,
                              uint32_t *vals_unsorted, uint32_t *keys_sorted, uint32_t *point_list, uint2 *ranges,
-                             char *temp, size_t temp_bytes, cudaStream_t stream)
+                             uint32_t *tile_order, char *temp, size_t temp_bytes, cudaStream_t stream)
 {
     cudaError_t e = cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream);
-    if (e != cudaSuccess || R == 0 || P == 0) return e;
+    const int rows = gy > row_offset ? (gy - row_offset + row_stride - 1) / row_stride : 0;
+    if (e != cudaSuccess) return e;
+    if (R == 0 || P == 0) {
+        if (rows > 0) order_tiles_kernel<<<1, 1024, 0, stream>>>(gx, rows, row_offset, row_stride, ranges, tile_order);
+        return cudaGetLastError();
+    }
     emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, gy, row_offset, row_stride, rec, radii,
                                                                idx_sorted, offsets, keys_unsorted, vals_unsorted);
     int bits = 1;
@@ -161,6 +194,7 @@ cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, i
                                         bits, stream);
     if (e != cudaSuccess) return e;
     tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, keys_sorted, ranges);
+    if (rows > 0) order_tiles_kernel<<<1, 1024, 0, stream>>>(gx, rows, row_offset, row_stride, ranges, tile_order);
     return cudaGetLastError();
 }
 

@@ -73,6 +73,7 @@ struct ImageView {
     float *final_T;      // [3][HW]  T, M1, M2
     uint32_t *n_contrib; // [2][HW]  last contributor, median contributor
     uint32_t *tile_max_contrib; // [tiles] max over the tile's pixels of last contributor
+    uint32_t *tile_order;       // [tiles] launch order (longest lists first)
 };
 
 struct BinView {

@@ -46,13 +46,14 @@ cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, i
                              const int *radii,
                              const uint32_t *idx_sorted, const uint32_t *offsets, uint32_t *keys_unsorted,
                              uint32_t *vals_unsorted, uint32_t *keys_sorted, uint32_t *point_list, uint2 *ranges,
-                             char *temp, size_t temp_bytes, cudaStream_t stream);
+                             uint32_t *tile_order, char *temp, size_t temp_bytes, cudaStream_t stream);
 
 // ---- render (render_fwd.cu / render_bwd.cu) ----
 struct RenderFwdArgs {
     int W, H, gx, gy;
     int row_offset = 0, row_stride = 1;  // tile-row window rendered by this call
     const uint2 *ranges;
+    const uint32_t *tile_order;  // launch order of the window's tiles (longest lists first)
     const uint32_t *point_list;
     const float *rec;
     const float *bg;
@@ -68,6 +69,7 @@ struct RenderBwdArgs {
     int W, H, gx, gy;
     int row_offset = 0, row_stride = 1;
     const uint2 *ranges;
+    const uint32_t *tile_order;
     const uint32_t *point_list;
     const float *rec;
     const float *bg;

@@ -67,7 +67,7 @@ struct Butterfly {
 
 template <bool CULL>
 __global__ void __maxnreg__(96)
-render_bwd_kernel(const int W, const int H, const int gx, const int row_offset, const int row_stride,
+render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
                   const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
                   const float *__restrict__ bg, const float *__restrict__ final_Ts,
@@ -79,8 +79,8 @@ render_bwd_kernel(const int W, const int H, const int gx, const int row_offset, 
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    // blockIdx.x enumerates the tiles of this call's row window
-    const int tile = (row_offset + row_stride * ((int)blockIdx.x / gx)) * gx + (int)blockIdx.x % gx;
+    // blockIdx.x enumerates the tiles of this call's row window, longest instance lists first
+    const int tile = (int)tile_order[blockIdx.x];
     const uint2 range = ranges[tile];
     // only list positions [0, total) can have been blended by some pixel of this tile
     const int total = min((int)(range.y - range.x), (int)tile_max_contrib[tile]);
@@ -141,6 +141,7 @@ render_bwd_kernel(const int W, const int H, const int gx, const int row_offset, 
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
 
     const int my_slot = Butterfly<NV, 4>::slot(lane, 0, NV);
+    const int my_slot15 = Butterfly<15, 4>::slot(lane, 0, 15);  // without the three normal gradients
 
     // Depth / normal / median-depth / distortion upstream gradients are exactly zero for whole frames in
     // practice (train.py enables those losses late): skip their recurrences when no pixel of the warp has any.
@@ -287,8 +288,14 @@ render_bwd_kernel(const int W, const int H, const int gx, const int row_offset, 
                     }
                 }
                 if (__any_sync(0xffffffffu, valid)) {
-                    Butterfly<NV, 4>::run(v, lane);
-                    if (my_slot >= 0) red_add_f32(gacc + (size_t)ring.id[stage][jj] * GACC_FLOATS + my_slot, v[0]);
+                    float *dst = gacc + (size_t)ring.id[stage][jj] * GACC_FLOATS;
+                    if (aux_any) {
+                        Butterfly<NV, 4>::run(v, lane);
+                        if (my_slot >= 0) red_add_f32(dst + my_slot, v[0]);
+                    } else {  // v[15..17] (normal gradients) are identically zero: 16 shuffles instead of 20
+                        Butterfly<15, 4>::run(v, lane);
+                        if (my_slot15 >= 0) red_add_f32(dst + my_slot15, v[0]);
+                    }
                 }
             }
         }
@@ -304,11 +311,11 @@ void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
     const int tiles = a.gx * rows;
     if (tiles == 0) return;
     if (a.subtile_cull)
-        render_bwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.row_offset, a.row_stride, a.ranges, a.point_list, a.rec, a.bg,
+        render_bwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec, a.bg,
                                                            a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
                                                            a.dL_dothers, a.gacc);
     else
-        render_bwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.row_offset, a.row_stride, a.ranges, a.point_list, a.rec, a.bg,
+        render_bwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec, a.bg,
                                                             a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
                                                             a.dL_dothers, a.gacc);
 }

@@ -24,7 +24,7 @@ namespace surfel {
 
 template <bool CULL>
 __global__ void __launch_bounds__(TILE_THREADS)
-render_fwd_kernel(const int W, const int H, const int gx, const int row_offset, const int row_stride,
+render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
                   const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
                   const float *__restrict__ bg, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
@@ -36,8 +36,8 @@ render_fwd_kernel(const int W, const int H, const int gx, const int row_offset, 
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    // blockIdx.x enumerates the tiles of this call's row window
-    const int tile = (row_offset + row_stride * ((int)blockIdx.x / gx)) * gx + (int)blockIdx.x % gx;
+    // blockIdx.x enumerates the tiles of this call's row window, longest instance lists first
+    const int tile = (int)tile_order[blockIdx.x];
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
     const int nchunks = (total + CHUNK - 1) / CHUNK;
@@ -192,11 +192,11 @@ void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream)
     const int tiles = a.gx * rows;
     if (tiles == 0) return;
     if (a.subtile_cull)
-        render_fwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.row_offset, a.row_stride, a.ranges, a.point_list, a.rec,
+        render_fwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec,
                                                                     a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
                                                                     a.out_color, a.out_others);
     else
-        render_fwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.row_offset, a.row_stride, a.ranges, a.point_list, a.rec,
+        render_fwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec,
                                                                      a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
                                                                      a.out_color, a.out_others);
 }
