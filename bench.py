@@ -41,7 +41,7 @@ from streetunveiler_b200 import synthetic as syn  # noqa: E402
 METRIC = "M Gaussians/s fwd+bwd @1920x1280"
 UNIT = "MGaussians/s"
 P_PER_GPU = 2_000_000
-HAND_WRITTEN_LAUNCHES_PER_STEP = 6  # preprocess_fwd, emit_instances, tile_ranges, render_fwd, render_bwd, preprocess_bwd
+HAND_WRITTEN_LAUNCHES_PER_STEP = 7  # preprocess_fwd, emit_instances, tile_ranges, order_tiles, render_fwd, render_bwd, preprocess_bwd
 
 
 # ------------------------------------------------------------------------------------------------
@@ -146,10 +146,12 @@ class Workload:
 
     def __init__(self, P_total, seed, world, rank, device):
         self.cam = syn.cam_a()
-        scene = syn.street_scene(P_total, seed, 3)
-        if world > 1:  # shard by Gaussian index: rank r owns rows [r P/G, (r+1) P/G)
-            lo, hi = rank * (P_total // world), (rank + 1) * (P_total // world)
-            scene = {k: (v[lo:hi].contiguous() if isinstance(v, torch.Tensor) else v) for k, v in scene.items()}
+        if world == 1:
+            scene = syn.street_scene(P_total, seed, 3)
+        else:
+            # index shard r of a STREET(P_total) scene: the street distribution is i.i.d. per surfel, so each
+            # rank draws its own P_total/world surfels (seed + rank) instead of generating all of them
+            scene = syn.street_scene(P_total // world, seed * 1000 + rank, 3)
         self.host = scene
         self.crc = syn.scene_crc(scene)
         self.P = scene["means3D"].shape[0]
@@ -305,6 +307,9 @@ def run_ours(args):
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": int(ab), "ms_per_launch": round(stages[dom], 4)}
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     value = P_total / (ms_step * 1e-3) / 1e6
@@ -322,8 +327,9 @@ def run_ours(args):
         "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": HAND_WRITTEN_LAUNCHES_PER_STEP * args.steps,
-        "gpu_launches_note": "hand-written kernels per step: preprocess_fwd, emit_instances, tile_ranges, render_fwd, "
-                             "render_bwd, preprocess_bwd (+ cub radix-sort/scan launches and 2 memsets, not counted)",
+        "gpu_launches_note": "hand-written kernels per step: preprocess_fwd, emit_instances, tile_ranges, order_tiles, "
+                             "render_fwd, render_bwd, preprocess_bwd (+1 count_window_tiles per rank when sharded; cub "
+                             "radix-sort/scan launches and 2 memsets not counted)",
         "roofline": roof,
         "step_roofline": {"alg_bytes": int(step_bytes), "achieved_gbs": round(step_bytes / (ms_step * 1e-3) / 1e9, 2),
                           "frac_of_peak": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),

@@ -194,6 +194,11 @@ SURFEL_API int surfel_shard_backward(
     float *dL_dmean2D, float *dL_dnormal, float *dL_dopacity, float *dL_dcolor,
     float *dL_dmean3D, float *dL_dtransMat, float *dL_dsh, float *dL_dscale, float *dL_drot, void *stream);
 
+/* Test hook for the hand-written stable LSD radix sort used by the binning stage: sorts n
+ * (uint32 key, uint32 value) pairs on key bits [0, end_bit) into the *_out arrays (device pointers). */
+SURFEL_API int surfel_debug_sort_pairs(int64_t n, int end_bit, const uint32_t *keys_in, const uint32_t *vals_in,
+                                       uint32_t *keys_out, uint32_t *vals_out, void *stream);
+
 /* Debug view of the geometry scratch: per-Gaussian tile counts [P], depth-ordered ids [P], inclusive
  * offsets [P] (all uint32) and the packed 96-byte projected records [P,24] (fp32 words). Any output
  * may be NULL. */

@@ -581,6 +581,23 @@ int surfel_shard_backward(int P, int D, int M, int width, int height, const floa
     return 0;
 }
 
+int surfel_debug_sort_pairs(int64_t n, int end_bit, const uint32_t *keys_in, const uint32_t *vals_in,
+                            uint32_t *keys_out, uint32_t *vals_out, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n < 0 || end_bit < 1 || end_bit > 32) return fail("surfel_debug_sort_pairs", "bad arguments");
+    if (n == 0) return 0;
+    if (!keys_in || !vals_in || !keys_out || !vals_out) return fail("surfel_debug_sort_pairs", "NULL pointer");
+    char *temp = nullptr;
+    const size_t bytes = radix_sort_temp_bytes(n);
+    CK("temp alloc", cudaMalloc(&temp, bytes));
+    cudaError_t e = radix_sort_pairs(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, bytes, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(temp);
+    if (e != cudaSuccess) return fail_cuda("surfel_debug_sort_pairs", e);
+    return 0;
+}
+
 int surfel_debug_copy_geometry(int P, const char *geometry_buffer, uint32_t *tiles_touched_out,
                                uint32_t *idx_sorted_out, uint32_t *offsets_out, float *records_out, void *stream)
 {

@@ -11,51 +11,29 @@
 //      ceil(log2(tiles)) bits (14 bits at 1920x1280 -> 2 digit passes over 8 B/instance instead of
 //      6 passes over 12 B/instance).
 // Stability of both sorts keeps ties (equal depth bits) in ascending Gaussian id, exactly the
-// order cub's stable sort gives the reference.
-#include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
-
+// order cub's stable sort gives the reference.  The sort and scan themselves are
+// hand-written (radix_sort.cu); no library call remains on the path.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace surfel {
 
-struct TilesInDepthOrder {
-    const uint32_t *tiles_touched;
-    const uint32_t *idx_sorted;
-    __host__ __device__ __forceinline__ uint32_t operator()(const int i) const { return tiles_touched[idx_sorted[i]]; }
-};
-using TilesIter = thrust::transform_iterator<TilesInDepthOrder, thrust::counting_iterator<int>>;
-
 size_t depth_sort_temp_bytes(int P)
 {
-    size_t a = 0, b = 0;
-    uint32_t *n32 = nullptr;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, n32, n32, n32, n32, P > 0 ? P : 1);
-    TilesIter it(thrust::counting_iterator<int>(0), TilesInDepthOrder{nullptr, nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, b, it, n32, P > 0 ? P : 1);
+    const size_t a = radix_sort_temp_bytes(P), b = scan_temp_bytes(P);
     return (a > b ? a : b) + 256;
 }
 
-size_t tile_sort_temp_bytes(int64_t R)
-{
-    size_t a = 0;
-    uint32_t *n32 = nullptr;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, n32, n32, n32, n32, R > 0 ? R : 1);
-    return a + 256;
-}
+size_t tile_sort_temp_bytes(int64_t R) { return radix_sort_temp_bytes(R) + 256; }
 
 cudaError_t run_depth_order(int P, const uint32_t *depth_key, uint32_t *depth_key_sorted, const uint32_t *idx_in,
                             uint32_t *idx_sorted, const uint32_t *tiles_touched, uint32_t *offsets,
                             int64_t *num_rendered_dev, char *temp, size_t temp_bytes, cudaStream_t stream)
 {
     (void)num_rendered_dev;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, depth_key, depth_key_sorted, idx_in, idx_sorted, P,
-                                                    0, 32, stream);
+    cudaError_t e = radix_sort_pairs(depth_key, idx_in, depth_key_sorted, idx_sorted, P, 32, temp, temp_bytes, stream);
     if (e != cudaSuccess) return e;
-    TilesIter it(thrust::counting_iterator<int>(0), TilesInDepthOrder{tiles_touched, idx_sorted});
-    return cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, offsets, P, stream);
+    return inclusive_scan_gathered(P, tiles_touched, idx_sorted, offsets, temp, temp_bytes, stream);
 }
 
 // A tile-row window {y : y >= row_offset, (y - row_offset) % row_stride == 0} selects the tile rows a
@@ -190,8 +168,7 @@ cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, i
                                                                idx_sorted, offsets, keys_unsorted, vals_unsorted);
     int bits = 1;
     while ((1u << bits) < (uint32_t)(gx * gy)) bits++;
-    e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_unsorted, keys_sorted, vals_unsorted, point_list, R, 0,
-                                        bits, stream);
+    e = radix_sort_pairs(keys_unsorted, vals_unsorted, keys_sorted, point_list, R, bits, temp, temp_bytes, stream);
     if (e != cudaSuccess) return e;
     tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, keys_sorted, ranges);
     if (rows > 0) order_tiles_kernel<<<1, 1024, 0, stream>>>(gx, rows, row_offset, row_stride, ranges, tile_order);

@@ -32,6 +32,14 @@ struct PreprocessBwdArgs {
 };
 void launch_preprocess_bwd(const PreprocessBwdArgs &a, cudaStream_t stream);
 
+// ---- radix sort / scan (radix_sort.cu) ----
+size_t radix_sort_temp_bytes(int64_t n);
+cudaError_t radix_sort_pairs(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+                             int64_t n, int end_bit, char *temp, size_t temp_bytes, cudaStream_t stream);
+size_t scan_temp_bytes(int n);
+cudaError_t inclusive_scan_gathered(int n, const uint32_t *tiles_touched, const uint32_t *idx_sorted, uint32_t *offsets,
+                                    char *temp, size_t temp_bytes, cudaStream_t stream);
+
 // ---- binning (binning.cu) ----
 size_t depth_sort_temp_bytes(int P);
 size_t tile_sort_temp_bytes(int64_t R);

@@ -75,7 +75,8 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
                   const float *__restrict__ dL_dpixels, const float *__restrict__ dL_dothers,
                   float *__restrict__ gacc)
 {
-    __shared__ __align__(128) TileRing ring;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileRing<BWD_STAGES> &ring = *reinterpret_cast<TileRing<BWD_STAGES> *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -92,7 +93,7 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
     if (warp == CONSUMER_WARPS) {
         // producer: stream slot i <-> list position total-1-i (back to front)
         const uint32_t last = range.x + (uint32_t)(total - 1);
-        ring_produce<true>(ring, lane, total, point_list, rec, [last](int i) { return last - (uint32_t)i; });
+        ring_produce<true, BWD_STAGES>(ring, lane, total, point_list, rec, [last](int i) { return last - (uint32_t)i; });
         return;
     }
 
@@ -301,7 +302,7 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[stage]);
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        if (++stage == BWD_STAGES) { stage = 0; phase ^= 1u; }
     }
 }
 
@@ -310,12 +311,16 @@ void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
     const int rows = a.gy > a.row_offset ? (a.gy - a.row_offset + a.row_stride - 1) / a.row_stride : 0;
     const int tiles = a.gx * rows;
     if (tiles == 0) return;
+    {  // per device and cheap: opt in to more than 48 KB of dynamic shared memory
+        cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<BWD_STAGES>));
+        cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<BWD_STAGES>));
+    }
     if (a.subtile_cull)
-        render_bwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec, a.bg,
+        render_bwd_kernel<true><<<tiles, TILE_THREADS, sizeof(TileRing<BWD_STAGES>), stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec, a.bg,
                                                            a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
                                                            a.dL_dothers, a.gacc);
     else
-        render_bwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec, a.bg,
+        render_bwd_kernel<false><<<tiles, TILE_THREADS, sizeof(TileRing<BWD_STAGES>), stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec, a.bg,
                                                             a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
                                                             a.dL_dothers, a.gacc);
 }

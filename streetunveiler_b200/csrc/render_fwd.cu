@@ -8,7 +8,7 @@
 // What is different from the reference kernel:
 //   * one packed 96-B record per instance, gathered into shared memory by the TMA engine
 //     (cp.async.bulk + mbarrier transaction bytes) by a dedicated producer warp through a
-//     6-stage ring (tile_pipeline.cuh); colour lives in the record (the reference re-reads it from
+//     multi-stage ring (tile_pipeline.cuh); colour lives in the record (the reference re-reads it from
 //     global memory inside the inner loop, forward.cu:418); no __syncthreads per batch;
 //   * each consumer warp owns an 8x4 pixel block of the 16x16 tile and first *compacts* each chunk:
 //     32 instances are tested in parallel (one per lane) against the warp's block using the
@@ -31,7 +31,8 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
                   uint32_t *__restrict__ tile_max_contrib, float *__restrict__ out_color,
                   float *__restrict__ out_others)
 {
-    __shared__ __align__(128) TileRing ring;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileRing<FWD_STAGES> &ring = *reinterpret_cast<TileRing<FWD_STAGES> *>(smem_raw);
     __shared__ uint32_t s_max_contrib;
 
     const int tid = threadIdx.x;
@@ -48,7 +49,7 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
     if (warp == CONSUMER_WARPS) {
         // ------------------------------ producer warp ------------------------------
         const uint32_t base = range.x;
-        ring_produce<false>(ring, lane, total, point_list, rec, [base](int i) { return base + (uint32_t)i; });
+        ring_produce<false, FWD_STAGES>(ring, lane, total, point_list, rec, [base](int i) { return base + (uint32_t)i; });
         __syncthreads();
         return;
     }
@@ -154,7 +155,7 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[stage]);
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        if (++stage == FWD_STAGES) { stage = 0; phase ^= 1u; }
     }
 
     // per-tile maximum of last_contributor: lets the backward pass skip the untouched list tail
@@ -191,12 +192,16 @@ void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream)
     const int rows = a.gy > a.row_offset ? (a.gy - a.row_offset + a.row_stride - 1) / a.row_stride : 0;
     const int tiles = a.gx * rows;
     if (tiles == 0) return;
+    {  // per device and cheap: opt in to more than 48 KB of dynamic shared memory
+        cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<FWD_STAGES>));
+        cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<FWD_STAGES>));
+    }
     if (a.subtile_cull)
-        render_fwd_kernel<true><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec,
+        render_fwd_kernel<true><<<tiles, TILE_THREADS, sizeof(TileRing<FWD_STAGES>), stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec,
                                                                     a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
                                                                     a.out_color, a.out_others);
     else
-        render_fwd_kernel<false><<<tiles, TILE_THREADS, 0, stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec,
+        render_fwd_kernel<false><<<tiles, TILE_THREADS, sizeof(TileRing<FWD_STAGES>), stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec,
                                                                      a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
                                                                      a.out_color, a.out_others);
 }

@@ -13,8 +13,9 @@
 
 namespace surfel {
 
-constexpr int CHUNK = 64;            // records per stage
-constexpr int NSTAGE = 6;            // 6 * 64 * 96 B = 36 KB of records in flight per CTA
+constexpr int CHUNK = 64;            // records per stage (64 * 96 B = 6 KB)
+constexpr int FWD_STAGES = 6;        // forward: 4 CTAs/SM x 38 KB (deeper rings measured no faster)
+constexpr int BWD_STAGES = 8;        // backward: 2 CTAs/SM (register bound) x 50 KB
 constexpr int CONSUMER_WARPS = 8;
 constexpr int TILE_THREADS = (CONSUMER_WARPS + 1) * 32;
 
@@ -38,7 +39,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 
+template <int NSTAGE>
 struct TileRing {
+    static constexpr int kStages = NSTAGE;
     float rec[NSTAGE][CHUNK * REC_FLOATS];
     uint32_t id[NSTAGE][CHUNK];
     uint64_t full[NSTAGE];
@@ -47,7 +50,8 @@ struct TileRing {
     volatile int limit;       // chunks the producer will ever issue (lowered when every warp is done)
 };
 
-__device__ __forceinline__ void ring_init(TileRing &r, const int tid)
+template <int NSTAGE>
+__device__ __forceinline__ void ring_init(TileRing<NSTAGE> &r, const int tid)
 {
     if (tid == 0) {
 #pragma unroll
@@ -64,8 +68,8 @@ __device__ __forceinline__ void ring_init(TileRing &r, const int tid)
 
 // Producer warp body.  position(i) maps the i-th streamed slot to an index into point_list
 // (front-to-back for the forward, back-to-front for the backward).
-template <bool STORE_IDS, typename PosFn>
-__device__ __forceinline__ void ring_produce(TileRing &r, const int lane, const int total, const uint32_t *__restrict__ point_list,
+template <bool STORE_IDS, int NSTAGE, typename PosFn>
+__device__ __forceinline__ void ring_produce(TileRing<NSTAGE> &r, const int lane, const int total, const uint32_t *__restrict__ point_list,
                                              const float *__restrict__ rec, PosFn position)
 {
     const int nchunks = (total + CHUNK - 1) / CHUNK;
@@ -145,7 +149,8 @@ __device__ __forceinline__ void ring_produce(TileRing &r, const int lane, const 
 
 // Consumer side: wait until stage data landed.  A warp that is already done only recycles stages so
 // the producer can keep feeding the others; it leaves as soon as the producer announces the end.
-__device__ __forceinline__ bool ring_wait_or_quit(TileRing &r, const int lane, const int stage, const uint32_t phase, const int c)
+template <int NSTAGE>
+__device__ __forceinline__ bool ring_wait_or_quit(TileRing<NSTAGE> &r, const int lane, const int stage, const uint32_t phase, const int c)
 {
     while (true) {
         int st = 0;

@@ -177,3 +177,29 @@ def test_sharded_two_gpus_equals_single_gpu():
            "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multigpu_check.py"), "150000"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MULTIGPU_CHECK OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (33, 14), (2048, 14), (2049, 32), (300_001, 14), (1_000_003, 32), (5_500_000, 14)])
+def test_radix_sort_is_a_stable_sort(n, bits):
+    """The hand-written LSD radix sort (csrc/radix_sort.cu) against torch's stable sort: bit-exact."""
+    import ctypes as C
+    from streetunveiler_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(n)
+    hi = (1 << bits) if bits < 32 else (1 << 31)
+    keys = torch.randint(0, hi, (n,), generator=g, dtype=torch.int64)
+    if bits == 32:
+        keys = keys * 2 + torch.randint(0, 2, (n,), generator=g, dtype=torch.int64)   # exercise the top bit
+    if n > 1000:
+        keys[: n // 3] = keys[0]                                                      # many ties -> stability matters
+    vals = torch.arange(n, dtype=torch.int64)
+    k32 = (keys & 0xFFFFFFFF).to(torch.int64)
+    kin = torch.where(k32 >= 2 ** 31, k32 - 2 ** 32, k32).to(torch.int32).to(dev)
+    vin = vals.to(torch.int32).to(dev)
+    kout, vout = torch.empty_like(kin), torch.empty_like(vin)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(_lib.lib().surfel_debug_sort_pairs(n, bits, p(kin), p(vin), p(kout), p(vout),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sort")
+    order = torch.sort(keys, stable=True)[1]
+    assert torch.equal(vout.cpu().to(torch.int64), order)
+    assert torch.equal(kout.cpu().to(torch.int64) & 0xFFFFFFFF, keys[order])
