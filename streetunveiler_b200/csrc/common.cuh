@@ -26,14 +26,14 @@ constexpr float T_EPS = 0.0001f;              // forward.cu:389
 //   q1 = (Tv.y, Tv.z, Tw.x, Tw.y)
 //   q2 = (Tw.z, mean2D.x, mean2D.y, opacity)
 //   q3 = (n.x, n.y, n.z, r)
-//   q4 = (g, b, e.x, e.y)
-//   q5 = (M00, M01, M11, r2)
+//   q4 = (g, b, bbox, e.x)
+//   q5 = (e.y, M00, M01, M11)
 // (Tu,Tv,Tw) = rows of the splat->pixel homogeneous map (reference geomState.transMat,
 // rasterizer_impl.h:38), n = view-space normal flipped towards the camera, rgb = SH colour or
-// colors_precomp.  (e, M, r2) is the conservative footprint of {alpha >= 1/255} used for sub-tile
-// culling: the pixel p can only contribute if (p-e)^T M (p-e) <= 1 (perspective-correct ellipse
-// rho3d <= tau) or |p - mean2D|^2 <= r2 (low-pass disc rho2d <= tau), tau = 2 ln(255 opacity)
-// slightly inflated.  M = 0 encodes "cannot bound: always evaluate".
+// colors_precomp.  (bbox, e, M) is the conservative footprint of {alpha >= 1/255} used for sub-tile
+// culling: bbox = 4 x u8 bounds in 8-pixel units; inside it the pixel p can only contribute if
+// (p-e)^T M (p-e) <= 1 (perspective-correct ellipse rho3d <= tau) or |p - mean2D|^2 <= tau/2 (low-pass
+// disc rho2d <= tau), tau = 2 ln(255 opacity) slightly inflated.  M = 0: no ellipse bound (ill-conditioned).
 // ---------------------------------------------------------------------------------------------
 constexpr int REC_FLOATS = 24;
 constexpr int REC_BYTES = REC_FLOATS * 4;

@@ -87,59 +87,98 @@ __device__ __forceinline__ void tile_rect(const float px, const float py, const 
 
 // Conservative footprint of the region where this splat can reach alpha >= 1/255, i.e.
 // rho = min(rho3d, rho2d) <= tau = 2 ln(255 o):
-//   * rho2d <= tau is the disc |p - mean2D|^2 <= tau / 2,
-//   * rho3d <= tau is a conic in pixel space.  With pixel offsets (X,Y) from the projected centre c,
-//     the intersection point is p = a0 X + a1 Y + a2 with a0 = Tv' x Tw, a1 = Tw x Tu', a2 = Tu' x Tv'
-//     (Tu' = Tu - c.x Tw, Tv' = Tv - c.y Tw), and rho3d <= tau <=> p.x^2 + p.y^2 - tau p.z^2 <= 0.
-//     When the quadratic part is positive definite this is an ellipse (X-e)^T M (X-e) <= 1.
-// tau is inflated (x1.002 + 0.01) to absorb fp32 rounding of the per-pixel evaluation; the render
-// kernels additionally inflate the pixel block by half a pixel and accept up to 1.02.
-// out = (e.x, e.y, M00, M01, M11, r2);  M = 0: not boundable, always evaluate;  r2 < 0 and a far-away
-// centre: can never contribute.
+//   * rho2d <= tau is the disc |p - mean2D|^2 <= tau / 2 (the render kernels recompute tau from opacity),
+//   * rho3d <= tau is a conic in pixel space.  Two bounds of it are stored:
+//     (a) its axis-aligned bounding box from the same closed form the reference uses for the 3-sigma
+//         extent (forward.cu:119-145 with cutoff^2 = tau) -- numerically robust (no near-singular
+//         division), with explicit slack for the fp32 cancellation in c^2 - q -- united with the disc's
+//         box and quantised outward to 8x8-pixel units (4 x u8 in one word);
+//     (b) when well conditioned, the ellipse itself (X-e)^T M (X-e) <= 1: with pixel offsets (X,Y) from
+//         the projected centre c the intersection point is p = a0 X + a1 Y + a2, a0 = Tv' x Tw,
+//         a1 = Tw x Tu', a2 = Tu' x Tv' (Tu' = Tu - c.x Tw, Tv' = Tv - c.y Tw), and
+//         rho3d <= tau <=> p.x^2 + p.y^2 - tau p.z^2 <= 0.  Thin diagonal needles make the 2x2 system
+//         for the centre ill-conditioned (in fp32: errors of pixels against a sub-pixel minor axis), so
+//         it is solved in fp64 and the render kernels add an evaluation-error term to their threshold.
+// tau is inflated (x1.002 + 0.01) to absorb fp32 rounding of the per-pixel evaluation.
+// out: word0 = bbox (x0 | x1<<8 | y0<<16 | y1<<24, 8-px units, x1<x0: never contributes),
+//      (e.x, e.y, M00, M01, M11); M00 == 0: no ellipse bound.
 __device__ __forceinline__ void cull_footprint(const float Tm[3][3], const float mx, const float my,
-                                               const float opacity, float out[6])
+                                               const float opacity, const int W, const int H, uint32_t &bbox,
+                                               float out[5])
 {
-    out[0] = mx; out[1] = my; out[2] = 0.f; out[3] = 0.f; out[4] = 0.f; out[5] = 1e30f;  // default: always evaluate
+    const uint32_t BOX_ALL = 0u | (255u << 8) | (0u << 16) | (255u << 24), BOX_NONE = 1u | (0u << 8) | (1u << 16);
+    bbox = BOX_ALL;
+    out[0] = mx; out[1] = my; out[2] = 0.f; out[3] = 0.f; out[4] = 0.f;
     const float o255 = 255.0f * opacity;
     if (!(o255 >= 1.0f)) {
-        if (o255 < 0.999f) {  // o exp(<=0) < 1/255 for every pixel (1e-3 guard against rounding of the product)
-            out[0] = -1e30f; out[1] = -1e30f; out[2] = 1.f; out[4] = 1.f; out[5] = -1.f;
-        }
+        if (o255 < 0.999f) bbox = BOX_NONE;  // o exp(<=0) < 1/255 everywhere (1e-3 guard for the product's rounding)
         return;
     }
     const float tau = 2.0f * __logf(o255) * 1.002f + 0.01f;
     const float Tw[3] = {Tm[2][0], Tm[2][1], Tm[2][2]};
-    float Tu[3], Tv[3];
+
+    // ---- (a) bounding box ----
+    const float rl = sqrtf(0.5f * tau) + 0.5f;  // low-pass disc
+    float lx = mx - rl, hx = mx + rl, ly = my - rl, hy = my + rl;
+    const float tz2 = Tw[2] * Tw[2];
+    const float dd = tau * (Tw[0] * Tw[0] + Tw[1] * Tw[1]) - tz2;
+    if (!(dd < -1e-3f * tz2)) return;  // conic not safely bounded: evaluate everywhere
+    {
+        const float inv = 1.0f / dd;
+        const float f0 = tau * inv, f2 = -inv;
+        const float cx = f0 * (Tm[0][0] * Tw[0] + Tm[0][1] * Tw[1]) + f2 * Tm[0][2] * Tw[2];
+        const float cy = f0 * (Tm[1][0] * Tw[0] + Tm[1][1] * Tw[1]) + f2 * Tm[1][2] * Tw[2];
+        const float qx = f0 * (Tm[0][0] * Tm[0][0] + Tm[0][1] * Tm[0][1]) + f2 * Tm[0][2] * Tm[0][2];
+        const float qy = f0 * (Tm[1][0] * Tm[1][0] + Tm[1][1] * Tm[1][1]) + f2 * Tm[1][2] * Tm[1][2];
+        const float hx2 = cx * cx - qx, hy2 = cy * cy - qy;
+        if (!(hx2 == hx2 && hy2 == hy2 && fabsf(cx) < 1e7f && fabsf(cy) < 1e7f)) return;
+        // fp32 cancellation in c^2 - q: |error| <= ~1e-6 (c^2 + |q|); plus relative and absolute slack
+        const float sx2 = 1e-6f * (cx * cx + fabsf(qx)), sy2 = 1e-6f * (cy * cy + fabsf(qy));
+        const float ex = sqrtf(fmaxf(hx2 + sx2, 0.f)) * 1.002f + 0.75f;
+        const float ey = sqrtf(fmaxf(hy2 + sy2, 0.f)) * 1.002f + 0.75f;
+        lx = fminf(lx, cx - ex); hx = fmaxf(hx, cx + ex);
+        ly = fminf(ly, cy - ey); hy = fmaxf(hy, cy + ey);
+    }
+    {
+        const float x0 = fmaxf(floorf(lx), 0.f), y0 = fmaxf(floorf(ly), 0.f);
+        const float x1 = fminf(ceilf(hx), (float)(W - 1)), y1 = fminf(ceilf(hy), (float)(H - 1));
+        if (x1 < x0 || y1 < y0) { bbox = BOX_NONE; return; }
+        const uint32_t bx0 = min((uint32_t)x0 >> 3, 255u), bx1 = min((uint32_t)x1 >> 3, 255u);
+        const uint32_t by0 = min((uint32_t)y0 >> 3, 255u), by1 = min((uint32_t)y1 >> 3, 255u);
+        bbox = bx0 | (bx1 << 8) | (by0 << 16) | (by1 << 24);  // a clamped 255 means "to the image border"
+    }
+
+    // ---- (b) ellipse: solved in double precision (a thin diagonal needle makes the 2x2 system for the
+    //      centre lose ~1/aspect^2 of the digits; B200 has full-rate fp64 to spare in this kernel) ----
+    double Tu[3], Tv[3];
+    const double Twd[3] = {(double)Tw[0], (double)Tw[1], (double)Tw[2]};
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        Tu[i] = Tm[0][i] - mx * Tw[i];
-        Tv[i] = Tm[1][i] - my * Tw[i];
+        Tu[i] = (double)Tm[0][i] - (double)mx * Twd[i];
+        Tv[i] = (double)Tm[1][i] - (double)my * Twd[i];
     }
-    const float a0[3] = {Tv[1] * Tw[2] - Tv[2] * Tw[1], Tv[2] * Tw[0] - Tv[0] * Tw[2], Tv[0] * Tw[1] - Tv[1] * Tw[0]};
-    const float a1[3] = {Tw[1] * Tu[2] - Tw[2] * Tu[1], Tw[2] * Tu[0] - Tw[0] * Tu[2], Tw[0] * Tu[1] - Tw[1] * Tu[0]};
-    const float a2[3] = {Tu[1] * Tv[2] - Tu[2] * Tv[1], Tu[2] * Tv[0] - Tu[0] * Tv[2], Tu[0] * Tv[1] - Tu[1] * Tv[0]};
-    const float q00 = a0[0] * a0[0] + a0[1] * a0[1] - tau * a0[2] * a0[2];
-    const float q01 = a0[0] * a1[0] + a0[1] * a1[1] - tau * a0[2] * a1[2];
-    const float q11 = a1[0] * a1[0] + a1[1] * a1[1] - tau * a1[2] * a1[2];
-    const float q02 = a0[0] * a2[0] + a0[1] * a2[1] - tau * a0[2] * a2[2];
-    const float q12 = a1[0] * a2[0] + a1[1] * a2[1] - tau * a1[2] * a2[2];
-    const float q22 = a2[0] * a2[0] + a2[1] * a2[1] - tau * a2[2] * a2[2];
-    const float det = q00 * q11 - q01 * q01;
-    // positive definite with a comfortable margin, otherwise the conic is (nearly) unbounded
-    if (!(q00 > 0.f && q11 > 0.f && det > 1e-4f * q00 * q11)) return;
-    const float inv = 1.0f / det;
-    const float ex = (q01 * q12 - q11 * q02) * inv;
-    const float ey = (q01 * q02 - q00 * q12) * inv;
-    const float fmin = q22 + q02 * ex + q12 * ey;
-    if (!(fabsf(ex) < 1e6f && fabsf(ey) < 1e6f) || !(fmin == fmin)) return;
-    out[5] = 0.5f * tau;
-    if (!(fmin < 0.f)) {  // empty ellipse: only the low-pass disc can contribute
-        out[0] = -1e30f; out[1] = -1e30f; out[2] = 1.f; out[4] = 1.f;
-        return;
-    }
-    const float s = -1.0f / fmin;
-    out[0] = mx + ex; out[1] = my + ey;
-    out[2] = q00 * s; out[3] = q01 * s; out[4] = q11 * s;
+    const double td = (double)tau;
+    const double a0[3] = {Tv[1] * Twd[2] - Tv[2] * Twd[1], Tv[2] * Twd[0] - Tv[0] * Twd[2], Tv[0] * Twd[1] - Tv[1] * Twd[0]};
+    const double a1[3] = {Twd[1] * Tu[2] - Twd[2] * Tu[1], Twd[2] * Tu[0] - Twd[0] * Tu[2], Twd[0] * Tu[1] - Twd[1] * Tu[0]};
+    const double a2[3] = {Tu[1] * Tv[2] - Tu[2] * Tv[1], Tu[2] * Tv[0] - Tu[0] * Tv[2], Tu[0] * Tv[1] - Tu[1] * Tv[0]};
+    const double q00 = a0[0] * a0[0] + a0[1] * a0[1] - td * a0[2] * a0[2];
+    const double q01 = a0[0] * a1[0] + a0[1] * a1[1] - td * a0[2] * a1[2];
+    const double q11 = a1[0] * a1[0] + a1[1] * a1[1] - td * a1[2] * a1[2];
+    const double q02 = a0[0] * a2[0] + a0[1] * a2[1] - td * a0[2] * a2[2];
+    const double q12 = a1[0] * a2[0] + a1[1] * a2[1] - td * a1[2] * a2[2];
+    const double q22 = a2[0] * a2[0] + a2[1] * a2[1] - td * a2[2] * a2[2];
+    const double det = q00 * q11 - q01 * q01;
+    if (!(q00 > 0.0 && q11 > 0.0 && det > 1e-7 * q00 * q11)) return;
+    const double inv = 1.0 / det;
+    const double ex = (q01 * q12 - q11 * q02) * inv;
+    const double ey = (q01 * q02 - q00 * q12) * inv;
+    const double fmin = q22 + q02 * ex + q12 * ey;
+    if (!(fabs(ex) < 1e5 && fabs(ey) < 1e5) || !(fmin < 0.0)) return;  // (empty or odd conic: box only)
+    const double sc = -1.0 / fmin;
+    const float m00 = (float)(q00 * sc), m01 = (float)(q01 * sc), m11 = (float)(q11 * sc);
+    if (!(m00 > 0.f && m11 > 0.f && m00 < 1e12f && m11 < 1e12f)) return;
+    out[0] = (float)((double)mx + ex); out[1] = (float)((double)my + ey);
+    out[2] = m00; out[3] = m01; out[4] = m11;
 }
 
 // =============================================================================================
@@ -289,16 +328,17 @@ preprocess_fwd_kernel(const int P, const int D, const int M, const float *__rest
         }
 
         const float opacity = opacities[idx];
-        float fp[6];
-        cull_footprint(Tm, cx, cy, opacity, fp);
+        float fp[5];
+        uint32_t bbox;
+        cull_footprint(Tm, cx, cy, opacity, W, H, bbox, fp);
 
         float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)idx * REC_FLOATS);
         r4[0] = make_float4(Tm[0][0], Tm[0][1], Tm[0][2], Tm[1][0]);
         r4[1] = make_float4(Tm[1][1], Tm[1][2], Tm[2][0], Tm[2][1]);
         r4[2] = make_float4(Tm[2][2], cx, cy, opacity);
         r4[3] = make_float4(normal.x, normal.y, normal.z, rgb[0]);
-        r4[4] = make_float4(rgb[1], rgb[2], fp[0], fp[1]);
-        r4[5] = make_float4(fp[2], fp[3], fp[4], fp[5]);
+        r4[4] = make_float4(rgb[1], rgb[2], __uint_as_float(bbox), fp[0]);
+        r4[5] = make_float4(fp[1], fp[2], fp[3], fp[4]);
         clamped[idx] = (uint8_t)clamp_bits;
 
         radius_out = (int)radius;

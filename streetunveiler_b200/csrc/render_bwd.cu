@@ -102,7 +102,6 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
     const uint32_t pix_x = bx0 + (lane & 7), pix_y = by0 + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const float2 pixf = make_float2((float)pix_x, (float)pix_y);
-    const float rx0 = (float)bx0 - 0.5f, rx1 = (float)bx0 + 7.5f, ry0 = (float)by0 - 0.5f, ry1 = (float)by0 + 3.5f;
     const size_t HW = (size_t)W * H;
     const size_t pix_id = (size_t)W * pix_y + pix_x;
 
@@ -172,7 +171,7 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
                 if (j < n) {
                     const int pos = pos_first - lane;
                     hit = (uint32_t)pos < warp_last;
-                    if (CULL && hit) hit = block_may_contribute(sb + j * REC_FLOATS, rx0, rx1, ry0, ry1);
+                    if (CULL && hit) hit = block_may_contribute(sb + j * REC_FLOATS, bx0, by0);
                 }
                 mask = __ballot_sync(0xffffffffu, hit);
             }

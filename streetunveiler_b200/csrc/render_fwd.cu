@@ -60,7 +60,6 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
     const uint32_t pix_x = bx0 + (lane & 7), pix_y = by0 + (lane >> 3);
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const float2 pixf = make_float2((float)pix_x, (float)pix_y);
-    const float rx0 = (float)bx0 - 0.5f, rx1 = (float)bx0 + 7.5f, ry0 = (float)by0 - 0.5f, ry1 = (float)by0 + 3.5f;
 
     bool done = !inside;
     float T = 1.0f;
@@ -83,7 +82,7 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
                 uint32_t mask;
                 if (CULL) {
                     const int j = h + lane;
-                    const bool hit = (j < n) && block_may_contribute(sb + j * REC_FLOATS, rx0, rx1, ry0, ry1);
+                    const bool hit = (j < n) && block_may_contribute(sb + j * REC_FLOATS, bx0, by0);
                     mask = __ballot_sync(0xffffffffu, hit);
                 } else {
                     mask = (n - h >= 32) ? 0xffffffffu : ((1u << (n - h)) - 1u);

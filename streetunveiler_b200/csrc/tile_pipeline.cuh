@@ -161,37 +161,46 @@ __device__ __forceinline__ bool ring_wait_or_quit(TileRing<NSTAGE> &r, const int
     }
 }
 
-// Conservative test: can any pixel of the (half-pixel inflated) block [rx0,rx1]x[ry0,ry1] reach
-// alpha >= 1/255 for the splat whose record is at `rp`?  See preprocess.cu cull_footprint.
-__device__ __forceinline__ bool block_may_contribute(const float *rp, const float rx0, const float rx1, const float ry0,
-                                                     const float ry1)
+// Conservative test: can any pixel of the 8x4 block at (bx0, by0) reach alpha >= 1/255 for the splat
+// whose record is at `rp`?  See preprocess.cu cull_footprint: 8-px bounding box first, then the low-pass
+// disc and (when present) the ellipse against the block inflated by half a pixel, with a threshold
+// that grows with the fp32 evaluation error of the quadratic (large for distant needles).
+__device__ __forceinline__ bool block_may_contribute(const float *rp, const int bx0, const int by0)
 {
-    const float2 mean = make_float2(rp[9], rp[10]);  // words 9,10 are not 8-byte aligned
-    const float2 e = *reinterpret_cast<const float2 *>(rp + 18);
-    const float4 m = *reinterpret_cast<const float4 *>(rp + 20);  // M00, M01, M11, r2
-    // low-pass disc
-    const float dx = fmaxf(fmaxf(rx0 - mean.x, mean.x - rx1), 0.f);
-    const float dy = fmaxf(fmaxf(ry0 - mean.y, mean.y - ry1), 0.f);
-    if (dx * dx + dy * dy <= m.w) return true;
-    if (m.x == 0.f) return true;  // footprint could not be bounded
+    const uint32_t bb = __float_as_uint(rp[18]);
+    const uint32_t ux = (uint32_t)bx0 >> 3, uy = (uint32_t)by0 >> 3;
+    const uint32_t x0 = bb & 255u, x1 = (bb >> 8) & 255u, y0 = (bb >> 16) & 255u, y1 = bb >> 24;
+    // a stored 255 is a clamp: it stands for every unit >= 255
+    if (ux < x0 || (ux > x1 && x1 != 255u) || uy < y0 || (uy > y1 && y1 != 255u)) return false;
+    const float4 m = *reinterpret_cast<const float4 *>(rp + 20);  // e.y, M00, M01, M11
+    if (m.y == 0.f) return true;                                   // no ellipse bound: the box decides
+    const float rx0 = (float)bx0 - 0.5f, rx1 = (float)bx0 + 7.5f, ry0 = (float)by0 - 0.5f, ry1 = (float)by0 + 3.5f;
+    // low-pass disc |p - mean|^2 <= tau / 2 <= ln(255) (+ the same inflation as preprocess): 5.6 bounds it
+    const float mx = rp[9], my = rp[10];
+    const float dx = fmaxf(fmaxf(rx0 - mx, mx - rx1), 0.f);
+    const float dy = fmaxf(fmaxf(ry0 - my, my - ry1), 0.f);
+    if (dx * dx + dy * dy <= 5.6f) return true;
     // ellipse (X-e)^T M (X-e) <= 1: minimum of the convex quadratic over the rectangle
-    const float X0 = rx0 - e.x, X1 = rx1 - e.x, Y0 = ry0 - e.y, Y1 = ry1 - e.y;
+    const float ex = rp[19], ey = m.x, m00 = m.y, m01 = m.z, m11 = m.w;
+    const float X0 = rx0 - ex, X1 = rx1 - ex, Y0 = ry0 - ey, Y1 = ry1 - ey;
     if (X0 <= 0.f && X1 >= 0.f && Y0 <= 0.f && Y1 >= 0.f) return true;
-    const float ky = -m.y * __frcp_rn(m.z), kx = -m.y * __frcp_rn(m.x);
+    const float ky = -m01 * __frcp_rn(m11), kx = -m01 * __frcp_rn(m00);
     float gmin;
     {
         const float Ya = fminf(fmaxf(ky * X0, Y0), Y1), Yb = fminf(fmaxf(ky * X1, Y0), Y1);
-        const float ga = m.x * X0 * X0 + (2.f * m.y * X0 + m.z * Ya) * Ya;
-        const float gb = m.x * X1 * X1 + (2.f * m.y * X1 + m.z * Yb) * Yb;
+        const float ga = m00 * X0 * X0 + (2.f * m01 * X0 + m11 * Ya) * Ya;
+        const float gb = m00 * X1 * X1 + (2.f * m01 * X1 + m11 * Yb) * Yb;
         gmin = fminf(ga, gb);
     }
     {
         const float Xa = fminf(fmaxf(kx * Y0, X0), X1), Xb = fminf(fmaxf(kx * Y1, X0), X1);
-        const float ga = m.z * Y0 * Y0 + (2.f * m.y * Y0 + m.x * Xa) * Xa;
-        const float gb = m.z * Y1 * Y1 + (2.f * m.y * Y1 + m.x * Xb) * Xb;
+        const float ga = m11 * Y0 * Y0 + (2.f * m01 * Y0 + m00 * Xa) * Xa;
+        const float gb = m11 * Y1 * Y1 + (2.f * m01 * Y1 + m00 * Xb) * Xb;
         gmin = fminf(gmin, fminf(ga, gb));
     }
-    return gmin <= 1.02f;
+    // fp32 evaluation error of g: a few ulps of its largest term (2|M01 X Y| <= M00 X^2 + M11 Y^2)
+    const float ax = fmaxf(fabsf(X0), fabsf(X1)), ay = fmaxf(fabsf(Y0), fabsf(Y1));
+    return gmin <= 1.02f + 4e-6f * (m00 * ax * ax + m11 * ay * ay);
 }
 
 }  // namespace surfel

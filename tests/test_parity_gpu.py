@@ -2,6 +2,7 @@
 operator -> C ABI -> CUDA kernels; the checkers are (a) golden vectors captured from the unmodified
 reference extension, (b) the CPU oracle, (c) the reference extension itself when oracle/_ref
 travelled, (d) size-independent properties at the benchmark's full size."""
+import math
 import os
 
 import numpy as np
@@ -203,3 +204,39 @@ def test_radix_sort_is_a_stable_sort(n, bits):
     order = torch.sort(keys, stable=True)[1]
     assert torch.equal(vout.cpu().to(torch.int64), order)
     assert torch.equal(kout.cpu().to(torch.int64) & 0xFFFFFFFF, keys[order])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_subtile_culling_is_exact_on_adversarial_scenes(seed):
+    """Needle-like, huge, near-plane-grazing and tiny splats: the footprint test may only ever skip what the
+    reference's alpha test would skip, so forward outputs must not change by a single bit with culling off."""
+    from streetunveiler_b200 import _lib
+    g = torch.Generator().manual_seed(100 + seed)
+    P = 60_000
+    cam = syn.cam_tilted(640, 400, 520.0, yaw=0.3, pitch=-0.2)
+    sc = syn.box_scene(P, 40 + seed, 2)
+    z = torch.rand(P, generator=g)
+    sc["means3D"][:, 2] = torch.where(z < 0.3, 0.15 + z * 2.0, 1.0 + z * 12.0)          # many splats graze the near plane
+    sc["means3D"][:, :2] *= 2.0
+    ratio = torch.exp(torch.randn(P, generator=g) * 2.0)                                   # anisotropy up to ~1000:1
+    base = torch.exp(torch.randn(P, generator=g) * 1.2 + math.log(0.05))
+    sc["scales"] = torch.stack([base * ratio.sqrt(), base / ratio.sqrt()], 1).clamp(1e-4, 8.0).contiguous()
+    sc["opacities"] = torch.where(torch.rand(P, 1, generator=g) < 0.2, torch.rand(P, 1, generator=g) * 0.01,
+                                  torch.rand(P, 1, generator=g)).contiguous()              # some below 1/255
+    grads = syn.upstream_grads(cam.width, cam.height, "all", seed=5)
+    a = hz.run_ours(sc, cam, bg=torch.tensor([0.2, 0.4, 0.6]), grads=grads)
+    _lib.set_option("subtile_cull", 0)
+    try:
+        b = hz.run_ours(sc, cam, bg=torch.tensor([0.2, 0.4, 0.6]), grads=grads)
+    finally:
+        _lib.set_option("subtile_cull", 1)
+    assert a["num_rendered"] == b["num_rendered"] and a["num_rendered"] > 0
+    for k in ("color", "allmap", "radii"):
+        assert np.array_equal(a[k], b[k]), k
+    for k, v in hz.compare(a, b).items():
+        assert v <= 2e-5, (k, v)
+    if hz.reference_available():
+        r = hz.run_reference(sc, cam, bg=torch.tensor([0.2, 0.4, 0.6]), grads=grads)
+        assert np.array_equal(a["radii"], r["radii"]) and a["num_rendered"] == r["num_rendered"]
+        for k, v in hz.compare(a, r).items():
+            assert v <= TOL, (k, v)
