@@ -41,7 +41,9 @@ from streetunveiler_b200 import synthetic as syn  # noqa: E402
 METRIC = "M Gaussians/s fwd+bwd @1920x1280"
 UNIT = "MGaussians/s"
 P_PER_GPU = 2_000_000
-HAND_WRITTEN_LAUNCHES_PER_STEP = 7  # preprocess_fwd, emit_instances, tile_ranges, order_tiles, render_fwd, render_bwd, preprocess_bwd
+# preprocess_fwd, 6 radix passes x (histogram, row scan, scatter), 3 scan kernels, emit_instances, tile_ranges,
+# order_tiles, render_fwd, render_bwd, preprocess_bwd -- every one hand-written (no library kernels on the path)
+HAND_WRITTEN_LAUNCHES_PER_STEP = 1 + 6 * 3 + 3 + 1 + 1 + 1 + 1 + 1 + 1
 
 
 # ------------------------------------------------------------------------------------------------
@@ -334,9 +336,9 @@ def run_ours(args):
         "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": HAND_WRITTEN_LAUNCHES_PER_STEP * args.steps,
-        "gpu_launches_note": "hand-written kernels per step: preprocess_fwd, emit_instances, tile_ranges, order_tiles, "
-                             "render_fwd, render_bwd, preprocess_bwd (+1 count_window_tiles per rank when sharded; cub "
-                             "radix-sort/scan launches and 2 memsets not counted)",
+        "gpu_launches_note": "per step: preprocess_fwd, 6 radix-sort passes x 3 kernels, 3 scan kernels, emit_instances, "
+                             "tile_ranges, order_tiles, render_fwd, render_bwd, preprocess_bwd (+1 count_window_tiles per "
+                             "rank when sharded; 2 memsets not counted); all hand-written, see profiles/r01_launches_final.md",
         "roofline": roof,
         "step_roofline": {"alg_bytes": int(step_bytes), "achieved_gbs": round(step_bytes / (ms_step * 1e-3) / 1e9, 2),
                           "frac_of_peak": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),

@@ -555,116 +555,94 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
     }
 
     // ---- SH VJP (backward.cu:20-139); also writes the zero rows of culled Gaussians ----
-    // The SH row of a Gaussian (12 M bytes) is read and its gradient row written with 128-bit
-    // accesses whenever rows are 16-byte aligned (M % 4 == 0, e.g. the M = 16 of degree 3).
+    // Streaming formulation: the row is visited once in memory order, four floats (one 128-bit access
+    // when rows are 16-byte aligned) at a time; element i = 3k + c needs only the k-th basis value and
+    // its gradient, which are compile-time selected polynomials of the view direction.  No 48-float
+    // staging arrays -> ~half the registers of the direct transcription.
     if (have_sh) {
         float *dsh = dL_dsh + (size_t)idx * M * 3;
         const float *sh = shs + (size_t)idx * M * 3;
-        const bool vec_ok = ((M & 3) == 0) && M <= 16 && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0) &&
+        const bool vec_ok = ((M & 3) == 0) && ((reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0) &&
                             ((reinterpret_cast<uintptr_t>(shs) & 15) == 0);
+        const int nflt = 3 * M;
         if (!visible) {
             if (vec_ok) {
                 float4 *d4 = reinterpret_cast<float4 *>(dsh);
-                for (int i = 0; i < (3 * M) / 4; i++) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < nflt / 4; i++) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
-                for (int i = 0; i < 3 * M; i++) dsh[i] = 0.f;
+                for (int i = 0; i < nflt; i++) dsh[i] = 0.f;
             }
         } else {
             const float len = sqrtf(dot3(dirx, diry, dirz, dirx, diry, dirz));
             const float x = dirx / len, y = diry / len, z = dirz / len;
-            const int ncoef = (D + 1) * (D + 1);
-            float shl[48], dl[48];
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            const int nact = 3 * (D + 1) * (D + 1);  // floats of the active coefficients
+            float gx[3] = {0.f, 0.f, 0.f}, gy[3] = {0.f, 0.f, 0.f}, gz[3] = {0.f, 0.f, 0.f};  // dRGB/d(dir)
 #pragma unroll
-            for (int i = 0; i < 48; i++) dl[i] = 0.f;
-            if (vec_ok) {
-                const float4 *s4 = reinterpret_cast<const float4 *>(sh);
+            for (int j = 0; j < 12; j++) {
+                if (4 * j < nflt) {
+                    float v[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+                    if (4 * j < nact) {
+                        if (vec_ok) {
+                            const float4 t = __ldg(reinterpret_cast<const float4 *>(sh) + j);
+                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                        } else {
 #pragma unroll
-                for (int i = 0; i < 12; i++)
-                    if (i * 4 < ncoef * 3) {
-                        const float4 t = __ldg(s4 + i);
-                        shl[4 * i] = t.x; shl[4 * i + 1] = t.y; shl[4 * i + 2] = t.z; shl[4 * i + 3] = t.w;
-                    }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 48; i++)
-                    if (i < ncoef * 3) shl[i] = __ldg(sh + i);
-            }
-            float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
-#define SH(k, c) shl[3 * (k) + (c)]
-#define DSH(k, v)                                            \
-    {                                                        \
-        const float vv = (v);                                \
-        dl[3 * (k)] = vv * dRGB[0];                          \
-        dl[3 * (k) + 1] = vv * dRGB[1];                      \
-        dl[3 * (k) + 2] = vv * dRGB[2];                      \
-    }
-            DSH(0, kSH_C0);
-            if (D > 0) {
-                DSH(1, -kSH_C1 * y);
-                DSH(2, kSH_C1 * z);
-                DSH(3, -kSH_C1 * x);
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    dRGBdx[c] = -kSH_C1 * SH(3, c);
-                    dRGBdy[c] = -kSH_C1 * SH(1, c);
-                    dRGBdz[c] = kSH_C1 * SH(2, c);
-                }
-                if (D > 1) {
-                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                    DSH(4, kSH_C2[0] * xy);
-                    DSH(5, kSH_C2[1] * yz);
-                    DSH(6, kSH_C2[2] * (2.f * zz - xx - yy));
-                    DSH(7, kSH_C2[3] * xz);
-                    DSH(8, kSH_C2[4] * (xx - yy));
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        dRGBdx[c] += kSH_C2[0] * y * SH(4, c) + kSH_C2[2] * 2.f * -x * SH(6, c) + kSH_C2[3] * z * SH(7, c) +
-                                     kSH_C2[4] * 2.f * x * SH(8, c);
-                        dRGBdy[c] += kSH_C2[0] * x * SH(4, c) + kSH_C2[1] * z * SH(5, c) + kSH_C2[2] * 2.f * -y * SH(6, c) +
-                                     kSH_C2[4] * 2.f * -y * SH(8, c);
-                        dRGBdz[c] += kSH_C2[1] * y * SH(5, c) + kSH_C2[2] * 2.f * 2.f * z * SH(6, c) + kSH_C2[3] * x * SH(7, c);
-                    }
-                    if (D > 2) {
-                        DSH(9, kSH_C3[0] * y * (3.f * xx - yy));
-                        DSH(10, kSH_C3[1] * xy * z);
-                        DSH(11, kSH_C3[2] * y * (4.f * zz - xx - yy));
-                        DSH(12, kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
-                        DSH(13, kSH_C3[4] * x * (4.f * zz - xx - yy));
-                        DSH(14, kSH_C3[5] * z * (xx - yy));
-                        DSH(15, kSH_C3[6] * x * (xx - 3.f * yy));
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            dRGBdx[c] += (kSH_C3[0] * SH(9, c) * 3.f * 2.f * xy + kSH_C3[1] * SH(10, c) * yz +
-                                          kSH_C3[2] * SH(11, c) * -2.f * xy + kSH_C3[3] * SH(12, c) * -3.f * 2.f * xz +
-                                          kSH_C3[4] * SH(13, c) * (-3.f * xx + 4.f * zz - yy) +
-                                          kSH_C3[5] * SH(14, c) * 2.f * xz + kSH_C3[6] * SH(15, c) * 3.f * (xx - yy));
-                            dRGBdy[c] += (kSH_C3[0] * SH(9, c) * 3.f * (xx - yy) + kSH_C3[1] * SH(10, c) * xz +
-                                          kSH_C3[2] * SH(11, c) * (-3.f * yy + 4.f * zz - xx) +
-                                          kSH_C3[3] * SH(12, c) * -3.f * 2.f * yz + kSH_C3[4] * SH(13, c) * -2.f * xy +
-                                          kSH_C3[5] * SH(14, c) * -2.f * yz + kSH_C3[6] * SH(15, c) * -3.f * 2.f * xy);
-                            dRGBdz[c] += (kSH_C3[1] * SH(10, c) * xy + kSH_C3[2] * SH(11, c) * 4.f * 2.f * yz +
-                                          kSH_C3[3] * SH(12, c) * 3.f * (2.f * zz - xx - yy) +
-                                          kSH_C3[4] * SH(13, c) * 4.f * 2.f * xz + kSH_C3[5] * SH(14, c) * (xx - yy));
+                            for (int e = 0; e < 4; e++)
+                                if (4 * j + e < nact) v[e] = __ldg(sh + 4 * j + e);
                         }
                     }
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const int i = 4 * j + e, k = i / 3, c = i % 3;
+                        float bv = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+                        switch (k) {  // folded at compile time (j, e are unrolled)
+                            case 0: bv = kSH_C0; break;
+                            case 1: bv = -kSH_C1 * y; by = -kSH_C1; break;
+                            case 2: bv = kSH_C1 * z; bz = kSH_C1; break;
+                            case 3: bv = -kSH_C1 * x; bx = -kSH_C1; break;
+                            case 4: bv = kSH_C2[0] * xy; bx = kSH_C2[0] * y; by = kSH_C2[0] * x; break;
+                            case 5: bv = kSH_C2[1] * yz; by = kSH_C2[1] * z; bz = kSH_C2[1] * y; break;
+                            case 6: bv = kSH_C2[2] * (2.f * zz - xx - yy); bx = kSH_C2[2] * -2.f * x; by = kSH_C2[2] * -2.f * y;
+                                    bz = kSH_C2[2] * 4.f * z; break;
+                            case 7: bv = kSH_C2[3] * xz; bx = kSH_C2[3] * z; bz = kSH_C2[3] * x; break;
+                            case 8: bv = kSH_C2[4] * (xx - yy); bx = kSH_C2[4] * 2.f * x; by = kSH_C2[4] * -2.f * y; break;
+                            case 9: bv = kSH_C3[0] * y * (3.f * xx - yy); bx = kSH_C3[0] * 6.f * xy; by = kSH_C3[0] * 3.f * (xx - yy); break;
+                            case 10: bv = kSH_C3[1] * xy * z; bx = kSH_C3[1] * yz; by = kSH_C3[1] * xz; bz = kSH_C3[1] * xy; break;
+                            case 11: bv = kSH_C3[2] * y * (4.f * zz - xx - yy); bx = kSH_C3[2] * -2.f * xy;
+                                     by = kSH_C3[2] * (-3.f * yy + 4.f * zz - xx); bz = kSH_C3[2] * 8.f * yz; break;
+                            case 12: bv = kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); bx = kSH_C3[3] * -6.f * xz;
+                                     by = kSH_C3[3] * -6.f * yz; bz = kSH_C3[3] * 3.f * (2.f * zz - xx - yy); break;
+                            case 13: bv = kSH_C3[4] * x * (4.f * zz - xx - yy); bx = kSH_C3[4] * (-3.f * xx + 4.f * zz - yy);
+                                     by = kSH_C3[4] * -2.f * xy; bz = kSH_C3[4] * 8.f * xz; break;
+                            case 14: bv = kSH_C3[5] * z * (xx - yy); bx = kSH_C3[5] * 2.f * xz; by = kSH_C3[5] * -2.f * yz;
+                                     bz = kSH_C3[5] * (xx - yy); break;
+                            case 15: bv = kSH_C3[6] * x * (xx - 3.f * yy); bx = kSH_C3[6] * 3.f * (xx - yy);
+                                     by = kSH_C3[6] * -6.f * xy; break;
+                            default: break;
+                        }
+                        const bool act = i < nact;  // coefficients above the active degree: exact zeros
+                        o[e] = act ? bv * dRGB[c] : 0.f;
+                        if (act) {
+                            gx[c] += bx * v[e];
+                            gy[c] += by * v[e];
+                            gz[c] += bz * v[e];
+                        }
+                    }
+                    if (vec_ok) {
+                        reinterpret_cast<float4 *>(dsh)[j] = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            if (4 * j + e < nflt) dsh[4 * j + e] = o[e];
+                    }
                 }
             }
-#undef SH
-#undef DSH
-            // coefficients above the active degree keep their exact zeros
-            if (vec_ok) {
-                float4 *d4 = reinterpret_cast<float4 *>(dsh);
-#pragma unroll
-                for (int i = 0; i < 12; i++)
-                    if (i * 4 < 3 * M) d4[i] = make_float4(dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 48; i++)
-                    if (i < 3 * M) dsh[i] = dl[i];
-            }
-            const float ddx = dot3(dRGBdx[0], dRGBdx[1], dRGBdx[2], dRGB[0], dRGB[1], dRGB[2]);
-            const float ddy = dot3(dRGBdy[0], dRGBdy[1], dRGBdy[2], dRGB[0], dRGB[1], dRGB[2]);
-            const float ddz = dot3(dRGBdz[0], dRGBdz[1], dRGBdz[2], dRGB[0], dRGB[1], dRGB[2]);
+            for (int i = 48; i < nflt; i++) dsh[i] = 0.f;  // M > 16 (never produced by the reference's callers)
+            const float ddx = dot3(gx[0], gx[1], gx[2], dRGB[0], dRGB[1], dRGB[2]);
+            const float ddy = dot3(gy[0], gy[1], gy[2], dRGB[0], dRGB[1], dRGB[2]);
+            const float ddz = dot3(gz[0], gz[1], gz[2], dRGB[0], dRGB[1], dRGB[2]);
             // normalisation Jacobian (auxiliary.h:128-138); "+=" on top of the geometric term (quirk 6)
             const float sum2 = dirx * dirx + diry * diry + dirz * dirz;
             const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
