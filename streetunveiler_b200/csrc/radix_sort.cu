@@ -80,6 +80,8 @@ digit_scatter_kernel(const int64_t n, const uint32_t *__restrict__ keys_in, cons
     __shared__ uint32_t wcnt[RS_WARPS][256];   // per-warp running digit counts -> exclusive bases across warps
     __shared__ uint32_t gbase[256];            // global offset of (digit, this CTA)
     __shared__ uint32_t wsum[RS_WARPS];
+    __shared__ uint32_t dstart[256];           // start of each digit's run in CTA-sorted order
+    __shared__ uint32_t s_k[RS_TILE], s_v[RS_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; w++) wcnt[w][threadIdx.x] = 0;
@@ -124,7 +126,8 @@ digit_scatter_kernel(const int64_t n, const uint32_t *__restrict__ keys_in, cons
         __syncwarp();
     }
     __syncthreads();
-    // exclusive prefix of the per-warp counts over the warps, per digit (thread = digit)
+    // exclusive prefix of the per-warp counts over the warps, per digit (thread = digit); the digit's CTA
+    // total then gets an exclusive scan over the 256 digits = start of the digit's run in CTA-sorted order
     {
         uint32_t run = 0;
 #pragma unroll
@@ -133,16 +136,43 @@ digit_scatter_kernel(const int64_t n, const uint32_t *__restrict__ keys_in, cons
             wcnt[w][threadIdx.x] = run;
             run += c;
         }
+        uint32_t x = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += wsum[w];
+        dstart[threadIdx.x] = wb + x - run;
     }
     __syncthreads();
+    // stage the tile in CTA-sorted order in shared memory, then write it out with consecutive threads on
+    // consecutive output slots (runs of equal digits are contiguous in global memory -> coalesced stores)
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; r++) {
         const int64_t i = wbase + r * 32 + lane;
         if (i < n) {
             const uint32_t d = (k[r] >> shift) & 255u;
-            const uint32_t pos = gbase[d] + wcnt[warp][d] + rank[r];
-            keys_out[pos] = k[r];
-            vals_out[pos] = v[r];
+            const uint32_t lpos = dstart[d] + wcnt[warp][d] + rank[r];
+            s_k[lpos] = k[r];
+            s_v[lpos] = v[r];
+        }
+    }
+    __syncthreads();
+    const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+    const int nvalid = (int)((n - tile_base) < (int64_t)RS_TILE ? (n - tile_base) : (int64_t)RS_TILE);
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        const int lp = r * RS_THREADS + threadIdx.x;
+        if (lp < nvalid) {
+            const uint32_t kk = s_k[lp];
+            const uint32_t d = (kk >> shift) & 255u;
+            const uint32_t pos = gbase[d] + ((uint32_t)lp - dstart[d]);
+            keys_out[pos] = kk;
+            vals_out[pos] = s_v[lp];
         }
     }
 }
