@@ -165,13 +165,15 @@ class Workload:
         self.bg = torch.zeros(3, device=device)
 
 
-def make_step(mod, wl: Workload, sharded=None):
+def make_step(mod, wl: Workload, sharded=None, own_buffers=False):
     import harness as hz
     st = hz._settings(mod, wl.cam, torch.zeros(3), 3, 1.0, wl.device)
     rast = mod.GaussianRasterizer(st)
-    leaves = {k: wl.dev[k].detach().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    src = {k: (v.clone() if own_buffers else v) for k, v in wl.dev.items()}
+    leaves = {k: src[k].detach().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
     m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
-    state = {}
+    grads = (wl.grads[0].clone(), wl.grads[1].clone()) if own_buffers else wl.grads
+    state = {"grads": grads}
 
     def step():
         for t in list(leaves.values()) + [m2]:
@@ -182,7 +184,7 @@ def make_step(mod, wl: Workload, sharded=None):
         else:
             color, radii, allmap = sharded(leaves["means3D"], m2, leaves["opacities"], leaves["shs"], leaves["scales"],
                                            leaves["rotations"], st)
-        torch.autograd.backward([color, allmap], [wl.grads[0], wl.grads[1]])
+        torch.autograd.backward([color, allmap], [grads[0], grads[1]])
         state["color"], state["allmap"], state["radii"] = color, allmap, radii
         fn = color.grad_fn
         state["R"] = getattr(fn, "num_rendered", None)
@@ -212,29 +214,73 @@ def timed_loop(fn, steps, warmup, world, device):
     return ms / steps
 
 
-def measure_e2e(step, leaves, m2, wl, args, world, device):
+def measure_e2e(mod, wl, args, world, device, sharded=None):
     """Same metric through the operator with HOST buffers: every step copies all inputs (parameters and
-    upstream gradients) from pinned host memory, runs fwd+bwd, and copies every output and gradient back."""
+    upstream gradients) from pinned host memory to the device, runs fwd+bwd, and copies every output and
+    gradient back to pinned host memory.  Steps are software-pipelined over two device buffer sets and
+    three streams (H2D of step i+1 | compute of step i | D2H of step i-1), PCIe being full duplex."""
     pin = {k: v.pin_memory() for k, v in wl.host.items() if isinstance(v, torch.Tensor)}
     pin_g = [g.pin_memory() for g in wl.grads_host]
     h2d = sum(v.numel() * v.element_size() for v in pin.values()) + sum(g.numel() * 4 for g in pin_g)
-    out_host = {}
+    sets = [make_step(mod, wl, sharded, own_buffers=True) for _ in range(2)]
+    # compute stays on the default stream (the reference extension can only launch there); copies use side streams
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    s_comp = torch.cuda.default_stream(device)
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_comp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    out_host = [{}, {}]
 
-    def e2e_step():
-        for k in leaves:
-            leaves[k].data.copy_(pin[k], non_blocking=True)
-        wl.grads[0].copy_(pin_g[0], non_blocking=True)
-        wl.grads[1].copy_(pin_g[1], non_blocking=True)
-        s = step()
-        outs = {"color": s["color"], "allmap": s["allmap"], "radii": s["radii"], "g_means2D": m2.grad}
-        outs.update({"g_" + k: v.grad for k, v in leaves.items()})
-        for k, v in outs.items():
-            if k not in out_host:
-                out_host[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
-            out_host[k].copy_(v.detach(), non_blocking=True)
+    def one(i):
+        k = i % 2
+        step, leaves, m2, state = sets[k]
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_comp[k])          # the previous step on this buffer set has consumed its inputs
+            for name in leaves:
+                leaves[name].data.copy_(pin[name], non_blocking=True)
+            state["grads"][0].copy_(pin_g[0], non_blocking=True)
+            state["grads"][1].copy_(pin_g[1], non_blocking=True)
+            ev_in[k].record(s_in)
+        with torch.cuda.stream(s_comp):
+            s_comp.wait_event(ev_in[k])
+            s_comp.wait_event(ev_out[k])         # its previous results have left the device
+            st = step()
+            outs = {"color": st["color"], "allmap": st["allmap"], "radii": st["radii"], "g_means2D": m2.grad}
+            outs.update({"g_" + name: v.grad for name, v in leaves.items()})
+            for v in outs.values():
+                v.record_stream(s_out)
+            ev_comp[k].record(s_comp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_comp[k])
+            for name, v in outs.items():
+                if name not in out_host[k]:
+                    out_host[k][name] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                out_host[k][name].copy_(v.detach(), non_blocking=True)
+            ev_out[k].record(s_out)
 
-    ms = timed_loop(e2e_step, max(2, args.steps // 2), 1, world, device)
-    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+    steps = max(4, args.steps)
+    for i in range(2):
+        one(i)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(device)
+    e0.record(cur)
+    for s_ in (s_in, s_out):
+        s_.wait_stream(cur)
+    for i in range(steps):
+        one(i)
+    for s_ in (s_in, s_out):
+        cur.wait_stream(s_)
+    e1.record(cur)
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    d2h = sum(v.numel() * v.element_size() for v in out_host[0].values())
     return ms, int(h2d), int(d2h)
 
 
@@ -282,7 +328,7 @@ def run_ours(args):
         print("debug: R after timed loop", state["R"], file=sys.stderr)
 
     # ---- e2e: host (pinned) buffers in, results out, every step ----
-    ms_e2e, h2d, d2h = measure_e2e(step, leaves, m2, wl, args, world, device)
+    ms_e2e, h2d, d2h = measure_e2e(mod, wl, args, world, device, sharded)
     if os.environ.get("BENCH_DEBUG"):
         print("debug: R after e2e loop", state["R"], file=sys.stderr)
 
@@ -369,7 +415,7 @@ def run_reference(args, force_cpu=False):
         ms_step = timed_loop(step, args.steps, args.warmup, 1, device)
         clocks = sampler.stop()
         value = wl.P / (ms_step * 1e-3) / 1e6
-        ms_e2e, h2d, d2h = measure_e2e(step, leaves, m2, wl, args, 1, device)
+        ms_e2e, h2d, d2h = measure_e2e(hz.reference_module(), wl, args, 1, device)
         e2e = {"value": round(wl.P / (ms_e2e * 1e-3) / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 3),
                "note": "the reference is a CUDA extension too, so its host-buffer call needs the same PCIe copies as ours; "
