@@ -311,8 +311,8 @@ def run_ours(args):
     import harness as hz
     mod = hz.ours_module()
 
-    P_total = P_PER_GPU * world
-    wl = Workload(P_total, 1 if world == 1 else 2, world, rank, device)
+    P_total = (args.total // world) * world if args.total else P_PER_GPU * world
+    wl = Workload(P_total, 1 if (world == 1 and not args.total) else 2, world, rank, device)
     sharded = None
     if world > 1:
         from streetunveiler_b200.sharded import ShardedRasterizer
@@ -371,13 +371,14 @@ def run_ours(args):
     step_bytes = alg_bytes_step(wl.P, R, HW)
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "scaling": "strong" if args.total else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"STREET(P={P_total}, seed={1 if world == 1 else 2}) CAM-A 1920x1280 SH3, "
+        "config": {"workload": f"STREET(P={P_total}, seed={1 if (world == 1 and not args.total) else 2}) CAM-A 1920x1280 SH3, "
                                f"grads colour+alpha; BASELINE configs[2]" + ("" if world == 1 else
                                f"; index shards of {P_PER_GPU} surfels per GPU, record all-gather + tile-row windows + image all-reduce + gradient reduce-scatter over NCCL"),
-                   "P_total": P_total, "P_per_gpu": wl.P, "num_rendered": R, "visible": P_vis, "input_crc32": wl.crc,
-                   "l2": "inputs (464 MB/GPU) larger than the 126 MB L2; no explicit flush"},
+                   "P_total": P_total, "P_per_gpu": wl.P, "parallelism": f"index-shard x{world}" if world > 1 else "single", "num_rendered": R, "visible": P_vis, "input_crc32": wl.crc,
+                   "l2": "per-GPU inputs (232 B/surfel, 464 MB at 2M) larger than the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3)},
@@ -458,6 +459,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total", type=int, default=0,
+                    help="strong scaling: total surfels split over the ranks (BASELINE configs[4]: --total 8000000); "
+                         "default 0 = weak scaling with 2,000,000 surfels per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "ours":
