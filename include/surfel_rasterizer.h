@@ -194,6 +194,29 @@ SURFEL_API int surfel_shard_backward(
     float *dL_dmean2D, float *dL_dnormal, float *dL_dopacity, float *dL_dcolor,
     float *dL_dmean3D, float *dL_dtransMat, float *dL_dsh, float *dL_dscale, float *dL_drot, void *stream);
 
+/*
+ * ---------------------------------------------------------------------------------------------
+ * Fused render() epilogue (reference: gaussian_renderer/__init__.py:148-186 +
+ * utils/point_utils.py:8-37, ~15 PyTorch kernels each way).  One kernel forward, one backward.
+ *   allmap [7,H,W], viewmatrix [16] = world_view_transform (device), fx = W / (2 tan(FoVx/2)), fy likewise
+ *   forward  -> rend_normal [3,H,W] (world space), surf_depth [1,H,W], surf_normal [3,H,W] (alpha-weighted),
+ *               surf_point [3,H,W]; optionally copies of the pass-through planes rend_alpha / rend_dist
+ *   backward -> dL_dallmap [7,H,W] from the gradients of those outputs (every element written;
+ *               alpha == 0 pixels get 0/0 = NaN in channels 0,1 exactly like autograd in the reference)
+ * ---------------------------------------------------------------------------------------------
+ */
+SURFEL_API int surfel_epilogue_forward(int width, int height, const float *allmap, const float *viewmatrix,
+                                       float fx, float fy, float depth_ratio, float *rend_normal,
+                                       float *surf_depth, float *surf_normal, float *surf_point,
+                                       float *rend_alpha /* [1,H,W] copy of channel 1, or NULL */,
+                                       float *rend_dist /* [1,H,W] copy of channel 6, or NULL */, void *stream);
+SURFEL_API int surfel_epilogue_backward(int width, int height, const float *allmap, const float *surf_point,
+                                        const float *viewmatrix, float fx, float fy, float depth_ratio,
+                                        const float *g_rend_normal, const float *g_surf_depth,
+                                        const float *g_surf_normal, const float *g_surf_point,
+                                        const float *g_rend_alpha /* or NULL */, const float *g_rend_dist /* or NULL */,
+                                        float *dL_dallmap, void *stream);
+
 /* Test hook for the hand-written stable LSD radix sort used by the binning stage: sorts n
  * (uint32 key, uint32 value) pairs on key bits [0, end_bit) into the *_out arrays (device pointers). */
 SURFEL_API int surfel_debug_sort_pairs(int64_t n, int end_bit, const uint32_t *keys_in, const uint32_t *vals_in,

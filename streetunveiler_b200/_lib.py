@@ -39,6 +39,8 @@ SIGNATURES = {
     "surfel_window_backward": (_i, [_i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "surfel_shard_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_epilogue_forward": (_i, [_i, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_epilogue_backward": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_sort_pairs": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_copy_geometry": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_set_option": (_i, [C.c_char_p, _i]),

@@ -162,6 +162,8 @@ bool have_device()
 
 }  // namespace
 
+int surfel_internal_fail(const char *where, const char *what) { return fail(where, what); }
+
 extern "C" {
 
 int surfel_abi_version(void) { return SURFEL_ABI_VERSION; }

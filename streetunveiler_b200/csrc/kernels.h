@@ -4,6 +4,9 @@
 #include <stddef.h>
 #include <stdint.h>
 
+// sets the thread's last-error message (api.cu) and returns a non-zero code
+int surfel_internal_fail(const char *where, const char *what);
+
 namespace surfel {
 
 struct PreprocessFwdArgs {
