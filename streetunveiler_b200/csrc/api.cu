@@ -92,7 +92,6 @@ GeomView carve_geom(char *base, int P, size_t cub_bytes)
     g.idx_sorted = carve<uint32_t>(p, n);
     g.offsets = carve<uint32_t>(p, n);
     g.clamped = carve<uint8_t>(p, n);
-    g.num_rendered = carve<int64_t>(p, 1);
     g.cub_temp = carve<char>(p, cub_bytes);
     g.cub_temp_bytes = cub_bytes;
     return g;
@@ -270,7 +269,7 @@ int surfel_forward_prepare(int P, int D, int M, int width, int height, const flo
 
     StageClock clk_depth(st, 1);
     CK("depth order", run_depth_order(P, g.depth_key, g.depth_key_sorted, g.idx_in, g.idx_sorted, g.tiles_touched,
-                                      g.offsets, g.num_rendered, g.cub_temp, g.cub_temp_bytes, st));
+                                      g.offsets, nullptr, g.cub_temp, g.cub_temp_bytes, st));
     clk_depth.stop();
     STAGE("depth order");
 

@@ -63,7 +63,6 @@ struct GeomView {
     uint32_t *idx_sorted;    // [P]  Gaussian ids by (depth, id)
     uint32_t *offsets;       // [P]  inclusive scan of tiles_touched in sorted order
     uint8_t *clamped;        // [P]  bit c set <=> SH colour channel c was clamped at 0
-    int64_t *num_rendered;   // [1]
     char *cub_temp;
     size_t cub_temp_bytes;
 };
