@@ -78,8 +78,12 @@ def build_case(name: str):
         scene["scales"] = (scene["scales"] * 3).contiguous()
         return dict(scene=scene, cam=cam, bg=torch.zeros(3), grads=syn.upstream_grads(240, 160, "color_alpha", seed=106),
                     kw={})
+    if name == "config1_box10k":  # BASELINE.json configs[0] at full size: BOX(10k, seed 3), CAM-S 256x256, SH degree 0
+        cam = syn.cam_s()
+        scene = syn.box_scene(10_000, 3, 0)
+        return dict(scene=scene, cam=cam, bg=torch.zeros(3), grads=syn.upstream_grads(256, 256, "color_alpha"), kw={})
     raise KeyError(name)
 
 
 CASES = ["box_sh0", "box_sh3_tilt", "odd_size_sh2", "precomp_color", "precomp_transmat", "scale_modifier",
-         "street_small"]
+         "street_small", "config1_box10k"]

@@ -21,9 +21,9 @@ import harness as hz  # noqa: E402
 from cases import CASES, build_case  # noqa: E402
 
 
-def main(out_dir):
+def main(out_dir, only=None):
     os.makedirs(out_dir, exist_ok=True)
-    for name in CASES:
+    for name in (only or CASES):
         c = build_case(name)
         runs = [hz.run_reference(c["scene"], c["cam"], bg=c["bg"], grads=c["grads"], **c["kw"]) for _ in range(3)]
         ref = runs[0]
@@ -38,4 +38,4 @@ def main(out_dir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "_new"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "_new"), sys.argv[2:] or None)
