@@ -363,6 +363,11 @@ def run_ours(args):
                 "alg_bytes_per_launch": int(ab), "ms_per_launch": round(stages[dom], 4)}
 
     if world > 1:
+        from streetunveiler_b200 import sharded as _sh
+        if _sh.PHASE_MS and rank == 0:
+            import statistics
+            print("shard phases, median ms per call (sync'd):",
+                  {k: round(statistics.median(v), 3) for k, v in _sh.PHASE_MS.items()}, file=sys.stderr)
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if rank != 0:

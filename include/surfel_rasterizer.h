@@ -154,13 +154,15 @@ SURFEL_API int surfel_debug_copy_binning(int width, int height, int64_t num_rend
  * ("window": rows y with y >= row_offset and (y - row_offset) % row_stride == 0).  Call sequence
  * per rank (host side: streetunveiler_b200/sharded.py):
  *   surfel_shard_preprocess   own shard -> projected records [P,24] fp32, radii, depth keys, clamp bytes
- *   (all-gather of records / radii / depth keys over NCCL)
+ *   surfel_shard_compact      keep the rows that survived culling (radius > 0), index order preserved;
+ *                             slot[i] = compact row of Gaussian i.  Only these rows are exchanged.
+ *   (all-gather of compact records / radii / depth keys over NCCL, padded to the largest count)
  *   surfel_window_prepare     depth order of ALL gathered Gaussians, instance count of the own window
  *   surfel_window_render      binning + blend of the own tile rows into full-size image planes
  *   (all-gather of the image rows)
  *   surfel_window_backward    gradient records [P_total,20] of the own tile rows (zeroed by the call)
  *   (reduce-scatter of the gradient records to the owners of the Gaussians)
- *   surfel_shard_backward     own shard: gradient record -> parameter gradients
+ *   surfel_shard_backward     own shard: gradient record (row slot[i] if grad_slot is given) -> parameter gradients
  * Every per-pixel result is identical to the single-GPU path (same lists, same order).
  * ---------------------------------------------------------------------------------------------
  */
@@ -171,6 +173,14 @@ SURFEL_API int surfel_shard_preprocess(
     const float *viewmatrix, const float *projmatrix, const float *cam_pos,
     float tan_fovx, float tan_fovy, int prefiltered,
     int *radii, float *records, uint32_t *depth_keys, unsigned char *clamped, void *stream);
+/* Compaction: outputs have room for P rows; rows [count, P) of radii_c / depth_keys_c are set to the
+ * "culled" pattern (0 / 0xFFFFFFFF) so that any prefix of >= count rows can be exchanged as is.
+ * *count_dev (device int) receives the number of visible Gaussians; temp: surfel_shard_compact_bytes(P). */
+SURFEL_API size_t surfel_shard_compact_bytes(int P);
+SURFEL_API int surfel_shard_compact(
+    int P, const int *radii, const float *records, const uint32_t *depth_keys,
+    float *records_c, int *radii_c, uint32_t *depth_keys_c, uint32_t *slot, int *count_dev,
+    char *temp, void *stream);
 SURFEL_API size_t surfel_window_bytes(int P_total);
 SURFEL_API int surfel_window_prepare(
     int P_total, int width, int height, int row_offset, int row_stride,
@@ -191,6 +201,7 @@ SURFEL_API int surfel_shard_backward(
     const float *transMat_precomp, const float *viewmatrix, const float *projmatrix, const float *cam_pos,
     float tan_fovx, float tan_fovy,
     const int *radii, const float *records, const unsigned char *clamped, const float *grad_records,
+    const uint32_t *grad_slot /* NULL: grad_records row i belongs to Gaussian i */,
     float *dL_dmean2D, float *dL_dnormal, float *dL_dopacity, float *dL_dcolor,
     float *dL_dmean3D, float *dL_dtransMat, float *dL_dsh, float *dL_dscale, float *dL_drot, void *stream);
 

@@ -33,12 +33,14 @@ SIGNATURES = {
     "surfel_debug_copy_binning": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "surfel_shard_preprocess": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _i,
                                      _vp, _vp, _vp, _vp, _vp]),
+    "surfel_shard_compact_bytes": (C.c_size_t, [_i]),
+    "surfel_shard_compact": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_window_bytes": (C.c_size_t, [_i]),
     "surfel_window_prepare": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _i]),
     "surfel_window_render": (_i, [_i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "surfel_window_backward": (_i, [_i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "surfel_shard_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp,
-                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_epilogue_forward": (_i, [_i, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_epilogue_backward": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_sort_pairs": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -456,6 +456,33 @@ int surfel_shard_preprocess(int P, int D, int M, int width, int height, const fl
     return 0;
 }
 
+size_t surfel_shard_compact_bytes(int P)
+{
+    if (P < 0) { fail("surfel_shard_compact_bytes", "negative P"); return 0; }
+    return compact_temp_bytes(P);
+}
+
+int surfel_shard_compact(int P, const int *radii, const float *records, const uint32_t *depth_keys, float *records_c,
+                         int *radii_c, uint32_t *depth_keys_c, uint32_t *slot, int *count_dev, char *temp,
+                         void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0) return fail("surfel_shard_compact", "bad sizes");
+    if (!count_dev) return fail("surfel_shard_compact", "count_dev is NULL");
+    if (P == 0) {
+        cudaError_t e0 = cudaMemsetAsync(count_dev, 0, sizeof(int), st);
+        if (e0 != cudaSuccess) return fail_cuda("surfel_shard_compact", e0);
+        return 0;
+    }
+    if (!radii || !records || !depth_keys || !records_c || !radii_c || !depth_keys_c || !slot || !temp)
+        return fail("surfel_shard_compact", "NULL required pointer");
+    if (!aligned(records, 16) || !aligned(records_c, 16)) return fail("surfel_shard_compact", "alignment");
+    cudaError_t e = run_compact_visible(P, radii, records, depth_keys, records_c, radii_c, depth_keys_c, slot,
+                                        count_dev, temp, compact_temp_bytes(P), st);
+    if (e != cudaSuccess) return fail_cuda("surfel_shard_compact", e);
+    return 0;
+}
+
 size_t surfel_window_bytes(int P_total)
 {
     if (P_total < 0) { fail("surfel_window_bytes", "negative P"); return 0; }
@@ -552,9 +579,9 @@ int surfel_shard_backward(int P, int D, int M, int width, int height, const floa
                           const float *scales, const float *rotations, const float *transMat_precomp,
                           const float *viewmatrix, const float *projmatrix, const float *cam_pos, float tan_fovx,
                           float tan_fovy, const int *radii, const float *records, const unsigned char *clamped,
-                          const float *grad_records, float *dL_dmean2D, float *dL_dnormal, float *dL_dopacity,
-                          float *dL_dcolor, float *dL_dmean3D, float *dL_dtransMat, float *dL_dsh, float *dL_dscale,
-                          float *dL_drot, void *stream)
+                          const float *grad_records, const uint32_t *grad_slot, float *dL_dmean2D, float *dL_dnormal,
+                          float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D, float *dL_dtransMat, float *dL_dsh,
+                          float *dL_dscale, float *dL_drot, void *stream)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (P < 0 || width <= 0 || height <= 0) return fail("surfel_shard_backward", "bad sizes");
@@ -572,7 +599,7 @@ int surfel_shard_backward(int P, int D, int M, int width, int height, const floa
     a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
     a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
     a.transMat_precomp = transMat_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
-    a.radii = radii; a.clamped = clamped; a.rec = records; a.gacc = grad_records;
+    a.radii = radii; a.clamped = clamped; a.rec = records; a.gacc = grad_records; a.gacc_slot = grad_slot;
     a.dL_dmean2D = dL_dmean2D; a.dL_dnormal = dL_dnormal; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
     a.dL_dmean3D = dL_dmean3D; a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale;
     a.dL_drot = dL_drot;

@@ -30,6 +30,7 @@ struct PreprocessBwdArgs {
     const int *radii;
     const uint8_t *clamped;
     const float *rec, *gacc;
+    const uint32_t *gacc_slot = nullptr;  // optional: row of gacc that belongs to Gaussian i (compact layout)
     float *dL_dmean2D, *dL_dnormal, *dL_dopacity, *dL_dcolor, *dL_dmean3D, *dL_dtransMat, *dL_dsh, *dL_dscale,
         *dL_drot;
 };
@@ -42,6 +43,12 @@ cudaError_t radix_sort_pairs(const uint32_t *keys_in, const uint32_t *vals_in, u
 size_t scan_temp_bytes(int n);
 cudaError_t inclusive_scan_gathered(int n, const uint32_t *tiles_touched, const uint32_t *idx_sorted, uint32_t *offsets,
                                     char *temp, size_t temp_bytes, cudaStream_t stream);
+
+// ---- visible-row compaction for the sharded path (compact.cu) ----
+size_t compact_temp_bytes(int P);
+cudaError_t run_compact_visible(int P, const int *radii, const float *rec, const uint32_t *keys, float *rec_c,
+                                int *radii_c, uint32_t *keys_c, uint32_t *slot, int *count_dev, char *temp,
+                                size_t temp_bytes, cudaStream_t stream);
 
 // ---- binning (binning.cu) ----
 size_t depth_sort_temp_bytes(int P);

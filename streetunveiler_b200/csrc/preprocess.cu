@@ -411,7 +411,8 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float focal_x, const float focal_y, const float tan_fovx, const float tan_fovy,
                       const float *__restrict__ cam_pos, const float *__restrict__ rec,
-                      const float *__restrict__ gacc, float *__restrict__ dL_dmean2D, float *__restrict__ dL_dnormal,
+                      const float *__restrict__ gacc, const uint32_t *__restrict__ gacc_slot, float *__restrict__ dL_dmean2D,
+                      float *__restrict__ dL_dnormal,
                       float *__restrict__ dL_dopacity, float *__restrict__ dL_dcolor, float *__restrict__ dL_dmean3D,
                       float *__restrict__ dL_dtransMat, float *__restrict__ dL_dsh, float2 *__restrict__ dL_dscale,
                       float4 *__restrict__ dL_drot)
@@ -430,7 +431,8 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
     float dirx = 0.f, diry = 0.f, dirz = 0.f;
 
     if (visible) {
-        const float4 *g4 = reinterpret_cast<const float4 *>(gacc + (size_t)idx * GACC_FLOATS);
+        const size_t row = gacc_slot ? (size_t)gacc_slot[idx] : (size_t)idx;  // compact rows in the sharded path
+        const float4 *g4 = reinterpret_cast<const float4 *>(gacc + row * GACC_FLOATS);
         const float4 a0 = g4[0], a1 = g4[1], a2 = g4[2], a3 = g4[3], a4 = g4[4];
         float dT[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};
         float dm2x = a2.y, dm2y = a2.z;
@@ -674,7 +676,7 @@ void launch_preprocess_bwd(const PreprocessBwdArgs &a, cudaStream_t stream)
     preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(
         a.P, a.D, a.M, a.means3D, a.radii, a.shs, a.clamped, reinterpret_cast<const float2 *>(a.scales),
         reinterpret_cast<const float4 *>(a.rotations), a.transMat_precomp, a.viewmatrix, a.projmatrix, a.focal_x,
-        a.focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, a.rec, a.gacc, a.dL_dmean2D, a.dL_dnormal, a.dL_dopacity,
+        a.focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, a.rec, a.gacc, a.gacc_slot, a.dL_dmean2D, a.dL_dnormal, a.dL_dopacity,
         a.dL_dcolor, a.dL_dmean3D, a.dL_dtransMat, a.dL_dsh, reinterpret_cast<float2 *>(a.dL_dscale),
         reinterpret_cast<float4 *>(a.dL_drot));
 }

@@ -5,15 +5,19 @@ is an ordered product, so a sum of per-shard images is not the re
 exact scheme used here keeps parameters, gradients and optimiser state sharded by Gaussian index and
 exchanges only *projected* data:
 
-  forward   1. every rank projects its own shard            (surfel_shard_preprocess, 96-B records)
-            2. all-gather of records / radii / depth keys   (NCCL over NVLink)
+  forward   1. every rank projects its own shard            (surfel_shard_preprocess, 96-B records) and keeps
+               the rows that survived culling, in index order (surfel_shard_compact) -- typically a
+               fifth of a street scene is in view, so the exchanges below shrink by that factor
+            2. all-gather of the compact records / radii / depth keys, padded to the largest count
+               (NCCL over NVLink; one tiny all-gather of the counts first)
             3. every rank bins + blends ALL Gaussians for its own tile rows (rows r, r+G, r+2G, ...;
                interleaved for load balance)               (surfel_window_prepare / _render)
             4. all-reduce(sum) of the ten image planes      (each rank wrote only its rows, the rest is 0)
   backward  5. every rank back-propagates its tile rows into 80-B gradient records of ALL Gaussians
                                                            (surfel_window_backward)
             6. reduce-scatter(sum) of the gradient records to the owners of the Gaussians
-            7. every rank turns its records into parameter gradients (surfel_shard_backward)
+            7. every rank turns its records into parameter gradients (surfel_shard_backward; Gaussian i
+               reads compact row slot[i])
 
 Every pixel sees exactly the list, order and arithmetic of the single-GPU path, so the forward is
 bit-identical to it and gradients differ only by float-add order.
@@ -31,6 +35,28 @@ import torch.distributed as dist
 
 REC_FLOATS = 24
 GREC_FLOATS = 20
+ROW_QUANTUM = 4096   # exchanged row counts are rounded up to this (stable buffer shapes from step to step)
+
+# SURFEL_SHARD_TIMING=1: synchronise around every phase and record wall-clock per phase and call (diagnostics only)
+import os as _os
+import time as _time
+_TIMING = _os.environ.get("SURFEL_SHARD_TIMING") == "1"
+PHASE_MS = {}
+
+
+class _phase:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMING:
+            torch.cuda.synchronize()
+            self.t = _time.perf_counter()
+
+    def __exit__(self, *a):
+        if _TIMING:
+            torch.cuda.synchronize()
+            PHASE_MS.setdefault(self.name, []).append((_time.perf_counter() - self.t) * 1e3)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -100,6 +126,22 @@ class NativeBackend:
             self._stream()), "surfel_shard_preprocess")
         return radii, rec, keys, clamped
 
+    def shard_compact(self, radii, rec, keys):
+        """-> (rec_c, radii_c, keys_c [P rows of capacity each], slot [P], count [1] int32 on the device)."""
+        P, dev = radii.shape[0], radii.device
+        rec_c = torch.empty_like(rec)
+        radii_c = torch.empty_like(radii)
+        keys_c = torch.empty_like(keys)
+        slot = torch.empty((P,), dtype=torch.int32, device=dev)
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        tmp = torch.empty((self._lib.size(self.L.surfel_shard_compact_bytes(P), "surfel_shard_compact_bytes"),),
+                          dtype=torch.uint8, device=dev)
+        p = self._p
+        self._lib.check(self.L.surfel_shard_compact(P, p(radii), p(rec), p(keys), p(rec_c), p(radii_c), p(keys_c),
+                                                    p(slot), C.c_void_p(count.data_ptr()), p(tmp), self._stream()),
+                        "surfel_shard_compact")
+        return rec_c, radii_c, keys_c, slot, count
+
     def window_forward(self, s, rec_all, radii_all, keys_all, row_offset, row_stride):
         L, p, dev = self.L, self._p, rec_all.device
         Pt, W, H = rec_all.shape[0], s.image_width, s.image_height
@@ -130,7 +172,7 @@ class NativeBackend:
             "surfel_window_backward")
         return grec
 
-    def shard_backward(self, s, means3D, shs, scales, rotations, radii, rec, clamped, grec):
+    def shard_backward(self, s, means3D, shs, scales, rotations, radii, rec, clamped, grec, slot):
         P, dev, M = means3D.shape[0], means3D.device, shs.shape[1]
         f32 = dict(dtype=torch.float32, device=dev)
         g = {"means2D": torch.empty((P, 3), **f32), "opacities": torch.empty((P, 1), **f32),
@@ -141,7 +183,7 @@ class NativeBackend:
         self._lib.check(self.L.surfel_shard_backward(
             P, int(s.sh_degree), M, s.image_width, s.image_height, p(means3D), p(shs), p(scales), p(rotations), None,
             p(s.viewmatrix), p(s.projmatrix), p(s.campos), float(s.tanfovx), float(s.tanfovy), p(radii), p(rec),
-            p(clamped), p(grec.contiguous()), p(g["means2D"]), None, p(g["opacities"]), p(g["colors"]), p(g["means3D"]),
+            p(clamped), p(grec.contiguous()), p(slot), p(g["means2D"]), None, p(g["opacities"]), p(g["colors"]), p(g["means3D"]),
             p(g["transMat"]), p(g["shs"]), p(g["scales"]), p(g["rotations"]), self._stream()), "surfel_shard_backward")
         return g
 
@@ -149,32 +191,43 @@ class NativeBackend:
 # ----------------------------------------------------------------------------------------------------
 class _ShardedRasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, shs, opacities, scales, rotations, settings, backend, group, p_max):
+    def forward(ctx, means3D, means2D, shs, opacities, scales, rotations, settings, backend, group):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        radii, rec, keys, clamped = backend.shard_preprocess(settings, means3D.contiguous(), shs.contiguous(),
-                                                             opacities.contiguous(), scales.contiguous(),
-                                                             rotations.contiguous())
-        # padded slots are culled Gaussians: radius 0, depth key 0xFFFFFFFF (sorts last, emits nothing)
-        rec_all = _all_gather_rows(pad_rows(rec, p_max), group)
-        radii_all = _all_gather_rows(pad_rows(radii, p_max), group)
-        keys_all = _all_gather_rows(pad_rows(keys, p_max, -1), group)
-        color, others, state = backend.window_forward(settings, rec_all, radii_all, keys_all, rank, world)
-        planes = torch.cat([color, others], 0)
-        dist.all_reduce(planes, group=group)               # every rank wrote only its tile rows
-        ctx.settings, ctx.backend, ctx.group, ctx.p_max, ctx.state = settings, backend, group, p_max, state
+        with _phase("fwd preprocess"):
+            radii, rec, keys, clamped = backend.shard_preprocess(settings, means3D.contiguous(), shs.contiguous(),
+                                                                 opacities.contiguous(), scales.contiguous(),
+                                                                 rotations.contiguous())
+            rec_c, radii_c, keys_c, slot, count = backend.shard_compact(radii, rec, keys)
+        # rows past a rank's count are culled Gaussians: radius 0, depth key 0xFFFFFFFF (sort last, emit nothing)
+        with _phase("fwd all-gather"):
+            counts = _all_gather_rows(count, group)
+            c_max = -(-max(int(counts.max().item()), 1) // ROW_QUANTUM) * ROW_QUANTUM   # the one host sync of the exchange
+            keep = min(c_max, rec_c.shape[0])
+            rec_all = _all_gather_rows(pad_rows(rec_c[:keep], c_max), group)
+            radii_all = _all_gather_rows(pad_rows(radii_c[:keep], c_max), group)
+            keys_all = _all_gather_rows(pad_rows(keys_c[:keep], c_max, -1), group)
+        with _phase("fwd window (sort+bin+blend)"):
+            color, others, state = backend.window_forward(settings, rec_all, radii_all, keys_all, rank, world)
+        with _phase("fwd image all-reduce"):
+            planes = torch.cat([color, others], 0)
+            dist.all_reduce(planes, group=group)               # every rank wrote only its tile rows
+        ctx.settings, ctx.backend, ctx.group, ctx.state = settings, backend, group, state
         ctx.num_rendered = state[0] if isinstance(state, tuple) else None
-        ctx.save_for_backward(means3D, shs, scales, rotations, radii, rec, clamped, rec_all)
+        ctx.save_for_backward(means3D, shs, scales, rotations, radii, rec, clamped, rec_all, slot)
         ctx.mark_non_differentiable(radii)
         return planes[:3].contiguous(), radii, planes[3:].contiguous()
 
     @staticmethod
     def backward(ctx, g_color, g_radii, g_others):
-        means3D, shs, scales, rotations, radii, rec, clamped, rec_all = ctx.saved_tensors
+        means3D, shs, scales, rotations, radii, rec, clamped, rec_all, slot = ctx.saved_tensors
         s, backend, group = ctx.settings, ctx.backend, ctx.group
-        grec_all = backend.window_backward(s, rec_all, ctx.state, g_color.contiguous(), g_others.contiguous())
-        grec = _reduce_scatter_rows(grec_all, group)[: means3D.shape[0]]
-        g = backend.shard_backward(s, means3D, shs, scales, rotations, radii, rec, clamped, grec)
-        return g["means3D"], g["means2D"], g["shs"], g["opacities"], g["scales"], g["rotations"], None, None, None, None
+        with _phase("bwd window blend"):
+            grec_all = backend.window_backward(s, rec_all, ctx.state, g_color.contiguous(), g_others.contiguous())
+        with _phase("bwd reduce-scatter"):
+            grec = _reduce_scatter_rows(grec_all, group)
+        with _phase("bwd per-Gaussian"):
+            g = backend.shard_backward(s, means3D, shs, scales, rotations, radii, rec, clamped, grec, slot)
+        return g["means3D"], g["means2D"], g["shs"], g["opacities"], g["scales"], g["rotations"], None, None, None
 
 
 class ShardedRasterizer:
@@ -189,17 +242,7 @@ class ShardedRasterizer:
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
         self.backend = backend if backend is not None else NativeBackend()
-        self._p_max = {}
-
-    def shard_rows(self, P_local: int, device) -> int:
-        """Common padded shard size (one tiny all-reduce the first time a shard size is seen)."""
-        if P_local not in self._p_max:
-            t = torch.tensor([P_local], dtype=torch.int64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            self._p_max[P_local] = int(t.item())
-        return self._p_max[P_local]
 
     def __call__(self, means3D, means2D, opacities, shs, scales, rotations, settings):
-        p_max = self.shard_rows(means3D.shape[0], means3D.device)
         return _ShardedRasterize.apply(means3D, means2D, shs, opacities, scales, rotations, settings, self.backend,
-                                       self.group, p_max)
+                                       self.group)

@@ -180,6 +180,27 @@ def test_sharded_two_gpus_equals_single_gpu():
     assert out.returncode == 0 and "MULTIGPU_CHECK OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
+@pytest.mark.parametrize("P,frac", [(1, 1.0), (5, 0.0), (1023, 0.5), (1024, 1.0), (1025, 0.3), (200_003, 0.2), (2_000_000, 0.05)])
+def test_shard_compaction_keeps_index_order(P, frac):
+    """surfel_shard_compact against boolean masking in torch: bit-exact rows, slots, count and tail pattern."""
+    from streetunveiler_b200.sharded import NativeBackend, REC_FLOATS
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(P)
+    vis = torch.rand(P, generator=g) < frac
+    radii = torch.where(vis, torch.randint(1, 500, (P,), generator=g), torch.zeros(P, dtype=torch.int64)).to(torch.int32)
+    rec = torch.randn(P, REC_FLOATS, generator=g)
+    keys = torch.randint(-2 ** 31, 2 ** 31 - 1, (P,), generator=g, dtype=torch.int64).to(torch.int32)
+    rec_c, radii_c, keys_c, slot, count = NativeBackend().shard_compact(radii.to(dev), rec.to(dev), keys.to(dev))
+    n = int(vis.sum())
+    assert int(count.item()) == n
+    assert torch.equal(rec_c[:n].cpu(), rec[vis]) and torch.equal(radii_c[:n].cpu(), radii[vis])
+    assert torch.equal(keys_c[:n].cpu(), keys[vis])
+    assert bool((radii_c[n:] == 0).all()) and bool((keys_c[n:] == -1).all())
+    want = torch.full((P,), -1, dtype=torch.int32)
+    want[vis] = torch.arange(n, dtype=torch.int32)
+    assert torch.equal(slot.cpu(), want)
+
+
 @pytest.mark.parametrize("n,bits", [(1, 8), (33, 14), (2048, 14), (2049, 32), (300_001, 14), (1_000_003, 32), (5_500_000, 14)])
 def test_radix_sort_is_a_stable_sort(n, bits):
     """The hand-written LSD radix sort (csrc/radix_sort.cu) against torch's stable sort: bit-exact."""

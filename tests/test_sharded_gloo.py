@@ -2,7 +2,7 @@
 
 The CUDA stages are replaced by a tiny differentiable torch "rasterizer" with the same backend
 interface, so what is exercised is the host logic: padding of unequal shards, all-gather order,
-tile-row windows (interleaved rows), image all-reduce, reduce-scatter of gradient records back to the
+tile-row windows (interleaved rows), compaction of the culled rows, image all-reduce, reduce-scatter of gradient records back to the
 owners, gradient routing.  The sharded result must equal the unsharded one."""
 import os
 import socket
@@ -26,15 +26,26 @@ class ToyBackend:
         rec[:, 0:2] = means3D[:, 0:2]
         rec[:, 2] = opacities[:, 0]
         rec[:, 3:6] = shs[:, 0, :]
-        radii = torch.ones(P, dtype=torch.int32)
+        radii = (means3D[:, 2] < 4.5).to(torch.int32)        # a few Gaussians are "culled": never exchanged
         keys = means3D[:, 2].contiguous().view(torch.int32).clone()
         return radii, rec, keys, torch.zeros(P, dtype=torch.uint8)
+
+    def shard_compact(self, radii, rec, keys):
+        P = radii.shape[0]
+        vis = radii > 0
+        n = int(vis.sum())
+        rec_c, radii_c, keys_c = torch.full_like(rec, float("nan")), torch.zeros_like(radii), torch.full_like(keys, -1)
+        rec_c[:n], radii_c[:n], keys_c[:n] = rec[vis], radii[vis], keys[vis]
+        slot = torch.full((P,), -1, dtype=torch.int32)
+        slot[vis] = torch.arange(n, dtype=torch.int32)
+        return rec_c, radii_c, keys_c, slot, torch.tensor([n], dtype=torch.int32)
 
     @staticmethod
     def _render(rec, radii, rows):
         ys = torch.tensor(rows, dtype=torch.float32)[:, None, None]
         xs = torch.arange(W, dtype=torch.float32)[None, :, None]
-        live = (radii > 0).float()[None, None, :]
+        live = (radii > 0)[None, None, :]
+        rec = torch.where((radii > 0)[:, None], rec, torch.zeros_like(rec))   # padded rows hold garbage
         w = live * rec[:, 2] * torch.exp(-((xs - rec[:, 0]) ** 2 + (ys - rec[:, 1]) ** 2) / 60.0)   # [rows, W, P]
         return torch.einsum("ywp,pc->cyw", w, rec[:, 3:6])
 
@@ -65,8 +76,12 @@ class ToyBackend:
             grec[:, :6] = grad[:, :6]
         return grec
 
-    def shard_backward(self, s, means3D, shs, scales, rotations, radii, rec, clamped, grec):
+    def shard_backward(self, s, means3D, shs, scales, rotations, radii, rec, clamped, grec, slot):
         P, M = means3D.shape[0], shs.shape[1]
+        vis = radii > 0
+        dense = torch.zeros(P, sharded.GREC_FLOATS)
+        dense[vis] = grec[slot[vis].long()]
+        grec = dense
         g = {"means3D": torch.zeros(P, 3), "means2D": torch.zeros(P, 3), "opacities": grec[:, 2:3].clone(),
              "shs": torch.zeros(P, M, 3), "scales": torch.zeros(P, 2), "rotations": torch.zeros(P, 4)}
         g["means3D"][:, 0:2] = grec[:, 0:2]
