@@ -199,9 +199,10 @@ class _ShardedRasterize(torch.autograd.Function):
                                                                  rotations.contiguous())
             rec_c, radii_c, keys_c, slot, count = backend.shard_compact(radii, rec, keys)
         # rows past a rank's count are culled Gaussians: radius 0, depth key 0xFFFFFFFF (sort last, emit nothing)
-        with _phase("fwd all-gather"):
+        with _phase("fwd counts"):
             counts = _all_gather_rows(count, group)
             c_max = -(-max(int(counts.max().item()), 1) // ROW_QUANTUM) * ROW_QUANTUM   # the one host sync of the exchange
+        with _phase("fwd all-gather"):
             keep = min(c_max, rec_c.shape[0])
             rec_all = _all_gather_rows(pad_rows(rec_c[:keep], c_max), group)
             radii_all = _all_gather_rows(pad_rows(radii_c[:keep], c_max), group)
