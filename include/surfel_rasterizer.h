@@ -228,6 +228,42 @@ SURFEL_API int surfel_epilogue_backward(int width, int height, const float *allm
                                         const float *g_rend_alpha /* or NULL */, const float *g_rend_dist /* or NULL */,
                                         float *dL_dallmap, void *stream);
 
+/*
+ * ---------------------------------------------------------------------------------------------
+ * Fused training-loss block (reference: utils/loss_utils.py:17-64 l1_loss / ssim and
+ * train.py:113-136, ~60 PyTorch kernels per iteration).  All images are dense fp32 [C,H,W] device arrays.
+ *
+ *   photometric:  img1 = render + sky * (1 - rend_alpha)   (train.py:113; sky == rend_alpha == NULL: img1 = render)
+ *                 out_means[0] = mean |img1 - gt|           (loss_utils.py:17-18)
+ *                 out_means[1] = mean ssim_map(img1, gt)    (loss_utils.py:33-64: window 11, sigma 1.5, zero padding,
+ *                                                            C1 = 0.01^2, C2 = 0.03^2, size_average = True)
+ *     forward   also writes deriv [9,H,W] (three maps per channel that the backward convolves; pass NULL when no
+ *               gradient is needed); scratch = surfel_loss_scratch_bytes(W, H) bytes; out_means = 2 floats (device).
+ *     backward  upstream = 2 floats (device): dL/d out_means[0], dL/d out_means[1]  -> d_render [3,H,W] and, with a
+ *               sky, d_rend_alpha [1,H,W] and d_sky [3,H,W] (either may be NULL).  Gradients w.r.t. gt are not produced.
+ *   regulariser:  out_means[0] = mean_p (1 - sum_c rend_normal * surf_normal)  (train.py:125-126)
+ *                 out_means[1] = mean rend_dist                                (train.py:134)
+ *     backward  upstream = 2 floats (device) -> d_rend_normal, d_surf_normal [3,H,W], d_rend_dist [1,H,W].
+ * The means are reduced in two deterministic stages (per-CTA fp32 partials, then one CTA in fp64): the same
+ * inputs give bit-identical results run to run.  No call synchronises the stream.
+ * ---------------------------------------------------------------------------------------------
+ */
+SURFEL_API size_t surfel_loss_scratch_bytes(int width, int height);
+SURFEL_API int surfel_loss_photometric_forward(int width, int height, const float *render, const float *rend_alpha,
+                                               const float *sky, const float *gt, float *deriv, char *scratch,
+                                               float *out_means, void *stream);
+SURFEL_API int surfel_loss_photometric_backward(int width, int height, const float *render, const float *rend_alpha,
+                                                const float *sky, const float *gt, const float *deriv,
+                                                const float *upstream, float *d_render, float *d_rend_alpha,
+                                                float *d_sky, void *stream);
+SURFEL_API int surfel_loss_regulariser_forward(int width, int height, const float *rend_normal,
+                                               const float *surf_normal, const float *rend_dist, char *scratch,
+                                               float *out_means, void *stream);
+SURFEL_API int surfel_loss_regulariser_backward(int width, int height, const float *rend_normal,
+                                                const float *surf_normal, const float *upstream,
+                                                float *d_rend_normal, float *d_surf_normal, float *d_rend_dist,
+                                                void *stream);
+
 /* Test hook for the hand-written stable LSD radix sort used by the binning stage: sorts n
  * (uint32 key, uint32 value) pairs on key bits [0, end_bit) into the *_out arrays (device pointers). */
 SURFEL_API int surfel_debug_sort_pairs(int64_t n, int end_bit, const uint32_t *keys_in, const uint32_t *vals_in,

@@ -43,6 +43,11 @@ SIGNATURES = {
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_epilogue_forward": (_i, [_i, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_epilogue_backward": (_i, [_i, _i, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_loss_scratch_bytes": (C.c_size_t, [_i, _i]),
+    "surfel_loss_photometric_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_loss_photometric_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_loss_regulariser_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_loss_regulariser_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_sort_pairs": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_copy_geometry": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_set_option": (_i, [C.c_char_p, _i]),
