@@ -264,6 +264,36 @@ SURFEL_API int surfel_loss_regulariser_backward(int width, int height, const flo
                                                 float *d_rend_normal, float *d_surf_normal, float *d_rend_dist,
                                                 void *stream);
 
+/*
+ * ---------------------------------------------------------------------------------------------
+ * Fused per-iteration parameter update.
+ *
+ * surfel_adam_step: what `gaussians.optimizer.step()` (train.py:197) does for the optimiser built at
+ * scene/gaussian_model.py:171-180 -- torch.optim.Adam over up to 8 single-tensor groups, each with its own
+ * learning rate and step count (no weight decay, no amsgrad) -- in ONE kernel launch: every parameter, gradient
+ * and moment element is read once and written once.  `groups` is a HOST array; the pointers inside are device
+ * pointers to dense fp32 arrays of n elements; `step` is the 1-based count of this update (torch's state["step"]
+ * after its increment).  The arithmetic follows torch/optim/adam.py (PyTorch 2.11) operation by operation.
+ *
+ * surfel_densification_stats: train.py:168 + scene/gaussian_model.py:555-557 in one launch, for the Gaussians with
+ * radii > 0:  max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum += ||viewspace_grad||_2;  denom += 1.
+ * radii [P] int32, viewspace_grad [P,3], max_radii2D [P], xyz_gradient_accum [P,1], denom [P,1] (fp32).
+ * ---------------------------------------------------------------------------------------------
+ */
+typedef struct surfel_adam_group {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    int64_t n;
+    double lr;   /* hyper-parameters are doubles, as in Python: 1 - beta2 must not be formed from a rounded fp32 beta2 */
+    int step;
+} surfel_adam_group;
+SURFEL_API int surfel_adam_step(int n_groups, const surfel_adam_group *groups, double beta1, double beta2, double eps,
+                                void *stream);
+SURFEL_API int surfel_densification_stats(int P, const int *radii, const float *viewspace_grad, float *max_radii2D,
+                                          float *xyz_gradient_accum, float *denom, void *stream);
+
 /* Test hook for the hand-written stable LSD radix sort used by the binning stage: sorts n
  * (uint32 key, uint32 value) pairs on key bits [0, end_bit) into the *_out arrays (device pointers). */
 SURFEL_API int surfel_debug_sort_pairs(int64_t n, int end_bit, const uint32_t *keys_in, const uint32_t *vals_in,

@@ -48,6 +48,8 @@ SIGNATURES = {
     "surfel_loss_photometric_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_loss_regulariser_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_loss_regulariser_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_adam_step": (_i, [_i, _vp, C.c_double, C.c_double, C.c_double, _vp]),
+    "surfel_densification_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_sort_pairs": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_copy_geometry": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_set_option": (_i, [C.c_char_p, _i]),
@@ -55,6 +57,12 @@ SIGNATURES = {
     "surfel_stage_name": (C.c_char_p, [_i]),
     "surfel_stage_time": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i)]),
 }
+
+
+class AdamGroup(C.Structure):
+    """struct surfel_adam_group (include/surfel_rasterizer.h)."""
+    _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", _i64), ("lr", C.c_double),
+                ("step", _i)]
 
 
 def build(verbose: bool = False) -> str:

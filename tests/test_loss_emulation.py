@@ -4,8 +4,6 @@ verifies halo / zero-padding / indexing / chain-rule logic of the very code the 
 the reference's loss functions and against the oracle -- the GPU tests then only have to confirm the parallel execution."""
 import ctypes as C
 import os
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
@@ -15,20 +13,6 @@ from loss_cases import LOSS_CASES, build_loss_case
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
-EMUL_DIR = os.path.join(HERE, "emul")
-NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-
-
-@pytest.fixture(scope="module")
-def emul():
-    if not os.path.exists(NVCC):
-        pytest.skip("nvcc not available")
-    so = os.path.join(EMUL_DIR, "libloss_emul.so")
-    srcs = [os.path.join(EMUL_DIR, "loss_emul.cu"), os.path.join(hz.ROOT, "streetunveiler_b200", "csrc", "loss_tile.cuh")]
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call([NVCC, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
-                               "-o", so, srcs[0]])
-    return C.CDLL(so)
 
 
 def _p(a):

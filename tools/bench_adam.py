@@ -1,0 +1,43 @@
+"""Fused parameter update vs torch.optim.Adam + the reference's statistics statements, 2M Gaussians (GPU box)."""
+import json, os, sys
+import torch
+from torch import nn
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from adam_cases import GROUPS, LRS, SHAPES
+from test_adam_gpu import torch_stats, fused_stats, make_optimizer
+from streetunveiler_b200.fused_adam import FusedAdam
+
+dev = torch.device("cuda")
+P = 2_000_000
+g = torch.Generator().manual_seed(1)
+
+def setup(cls):
+    params = {k: nn.Parameter(torch.randn((P,) + SHAPES[k], generator=g).to(dev)) for k in GROUPS}
+    grads = {k: (0.01 * torch.randn((P,) + SHAPES[k], generator=g)).to(dev) for k in GROUPS}
+    return params, grads, make_optimizer(cls, params)
+
+radii = torch.randint(0, 40, (P,), generator=g, dtype=torch.int32).to(dev)
+vgrad = (torch.randn(P, 3, generator=g) * 1e-3).to(dev)
+
+def timeit(cls, stats, n=20):
+    params, grads, opt = setup(cls)
+    mr, acc, dn = torch.zeros(P, device=dev), torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev)
+    def step():
+        for k in GROUPS: params[k].grad = grads[k]
+        stats(radii, vgrad, mr, acc, dn)
+        opt.step()
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): step()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+t_fused, t_torch = timeit(FusedAdam, fused_stats), timeit(torch.optim.Adam, torch_stats)
+alg = P * (58 * 28 + 4 + 12 + 3 * 8)     # 58 parameters x (p,m,v read+write, g read) + radii + grad + 3 statistics r/w
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+print(json.dumps({"op": "parameter update: Adam over 6 groups (58 floats/Gaussian) + densification statistics, 2M Gaussians",
+                  "fused_ms": round(t_fused, 4), "torch_ms": round(t_torch, 4), "speedup": round(t_torch / t_fused, 2),
+                  "alg_bytes": alg, "fused_gbs": round(alg / t_fused / 1e6, 1), "frac_of_hbm_peak": round(alg / t_fused / 1e6 / peak, 3)}))
