@@ -230,6 +230,40 @@ SURFEL_API int surfel_epilogue_backward(int width, int height, const float *allm
 
 /*
  * ---------------------------------------------------------------------------------------------
+ * Colour passes over ONE geometry / binning state.  The reference's render_semantic
+ * (gaussian_renderer/__init__.py:327-460) calls the rasterizer once per 3 semantic classes with identical geometry
+ * and different `colors_precomp` / `bg`, repeating projection, both sorts and binning every time, and autograd then
+ * runs one full backward per call.  Here the first pass is surfel_forward_prepare + surfel_forward_render with the
+ * first colour set; every further pass is
+ *     surfel_pass_set_colors  (rewrites the 12 colour bytes of each packed record)
+ *     surfel_pass_render      (blend only: same lists, same order -> out_color differs, out_others is identical)
+ * and the backward is, per pass in any order,
+ *     surfel_pass_set_colors; surfel_pass_backward_blend (clear = 1 for the first call only);
+ *     surfel_pass_take_color_grad (that pass's dL/dcolors_precomp, or NULL to discard; clears the colour words)
+ * followed by ONE surfel_pass_backward_geometry for the summed geometry gradients.  dL_dothers of a pass that
+ * contributed no allmap gradient is an all-zero [7,H,W] array.  Buffers are the ones of the forward calls.
+ * ---------------------------------------------------------------------------------------------
+ */
+SURFEL_API int surfel_pass_set_colors(int P, const float *colors_precomp, char *geometry_buffer, void *stream);
+SURFEL_API int surfel_pass_render(int P, int width, int height, int64_t num_rendered, const float *background,
+                                  char *geometry_buffer, char *binning_buffer, char *image_buffer, float *out_color,
+                                  float *out_others, void *stream, int debug);
+SURFEL_API int surfel_pass_backward_blend(int P, int width, int height, int64_t num_rendered, const float *background,
+                                          char *geometry_buffer, char *binning_buffer, char *image_buffer,
+                                          const float *dL_dpix, const float *dL_dothers, char *grad_scratch, int clear,
+                                          void *stream, int debug);
+SURFEL_API int surfel_pass_take_color_grad(int P, char *grad_scratch, float *dL_dcolor, void *stream);
+SURFEL_API int surfel_pass_backward_geometry(int P, int width, int height, const float *means3D, const float *scales,
+                                             const float *rotations, const float *transMat_precomp,
+                                             const float *viewmatrix, const float *projmatrix, const float *cam_pos,
+                                             float tan_fovx, float tan_fovy, const int *radii, char *geometry_buffer,
+                                             char *grad_scratch, float *dL_dmean2D, float *dL_dnormal,
+                                             float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D,
+                                             float *dL_dtransMat, float *dL_dscale, float *dL_drot, void *stream,
+                                             int debug);
+
+/*
+ * ---------------------------------------------------------------------------------------------
  * Fused training-loss block (reference: utils/loss_utils.py:17-64 l1_loss / ssim and
  * train.py:113-136, ~60 PyTorch kernels per iteration).  All images are dense fp32 [C,H,W] device arrays.
  *

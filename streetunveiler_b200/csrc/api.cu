@@ -159,6 +159,78 @@ bool have_device()
     return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
 }
 
+
+// K7 into the per-Gaussian gradient accumulator (optionally cleared first) ...
+int backward_blend(int P, int width, int height, int64_t num_rendered, const float *background, const GeomView &g,
+                   const ImageView &iv, const BinView &bv, const float *dL_dpix, const float *dL_dothers,
+                   char *grad_scratch, bool clear, cudaStream_t st, int debug)
+{
+    char *gp = grad_scratch;
+    float *gacc = carve<float>(gp, (size_t)P * GACC_FLOATS);
+    if (clear) CK("grad scratch clear", cudaMemsetAsync(gacc, 0, (size_t)P * GACC_FLOATS * sizeof(float), st));
+    if (num_rendered > 0) {
+        RenderBwdArgs r;
+        r.W = width; r.H = height;
+        r.gx = (width + TILE_X - 1) / TILE_X; r.gy = (height + TILE_Y - 1) / TILE_Y;
+        r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
+        r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
+        r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = gacc; r.subtile_cull = g_subtile_cull;
+        {
+            StageClock clk(st, 4);
+            launch_render_bwd(r, st);
+        }
+        STAGE("render backward");
+    }
+    return 0;
+}
+
+// ... and K8 from the accumulator to the parameter gradients.
+int backward_geometry(int P, int D, int M, int width, int height, const float *means3D, const float *shs,
+                      const float *scales, const float *rotations, const float *transMat_precomp,
+                      const float *viewmatrix, const float *projmatrix, const float *cam_pos, float tan_fovx,
+                      float tan_fovy, const int *radii, const GeomView &g, char *grad_scratch, float *dL_dmean2D,
+                      float *dL_dnormal, float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D, float *dL_dtransMat,
+                      float *dL_dsh, float *dL_dscale, float *dL_drot, cudaStream_t st, int debug)
+{
+    char *gp = grad_scratch;
+    float *gacc = carve<float>(gp, (size_t)P * GACC_FLOATS);
+    PreprocessBwdArgs a;
+    a.P = P; a.D = D; a.M = M;
+    a.focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:388-389
+    a.focal_x = width / (2.0f * tan_fovx);
+    a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+    a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
+    a.transMat_precomp = transMat_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
+    a.radii = radii; a.clamped = g.clamped; a.rec = g.rec; a.gacc = gacc;
+    a.dL_dmean2D = dL_dmean2D; a.dL_dnormal = dL_dnormal; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
+    a.dL_dmean3D = dL_dmean3D; a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale;
+    a.dL_drot = dL_drot;
+    {
+        StageClock clk(st, 5);
+        launch_preprocess_bwd(a, st);
+    }
+    STAGE("preprocess backward");
+    return 0;
+}
+
+// K6 over an existing binning state
+int render_pass(int width, int height, const float *background, const GeomView &g, const ImageView &iv,
+                const BinView &bv, float *out_color, float *out_others, cudaStream_t st, int debug)
+{
+    RenderFwdArgs r;
+    r.W = width; r.H = height;
+    r.gx = (width + TILE_X - 1) / TILE_X; r.gy = (height + TILE_Y - 1) / TILE_Y;
+    r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
+    r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
+    r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
+    {
+        StageClock clk(st, 3);
+        launch_render_fwd(r, st);
+    }
+    STAGE("render forward");
+    return 0;
+}
+
 }  // namespace
 
 int surfel_internal_fail(const char *where, const char *what) { return fail(where, what); }
@@ -307,17 +379,7 @@ int surfel_forward_render(int P, int width, int height, int64_t num_rendered, co
     clk_bin.stop();
     STAGE("tile binning");
 
-    RenderFwdArgs r;
-    r.W = width; r.H = height; r.gx = gx; r.gy = gy;
-    r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
-    r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
-    r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
-    {
-        StageClock clk(st, 3);
-        launch_render_fwd(r, st);
-    }
-    STAGE("render forward");
-    return 0;
+    return render_pass(width, height, background, g, iv, bv, out_color, out_others, st, debug);
 }
 
 int surfel_backward(int P, int D, int M, int64_t num_rendered, const float *background, int width, int height,
@@ -344,46 +406,102 @@ int surfel_backward(int P, int D, int M, int64_t num_rendered, const float *back
     if (!aligned(dL_dscale, 8) || !aligned(dL_drot, 16) || (scales && (!aligned(scales, 8) || !aligned(rotations, 16))))
         return fail("surfel_backward", "scale/rotation buffers must be 8/16-byte aligned");
 
-    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
     GeomView g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
     ImageView iv = carve_image(image_buffer, width, height);
     BinView bv{};
     if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
 
+    if (int rc = backward_blend(P, width, height, num_rendered, background, g, iv, bv, dL_dpix, dL_dothers, grad_scratch,
+                                /*clear=*/true, st, debug))
+        return rc;
+    return backward_geometry(P, D, M, width, height, means3D, shs, scales, rotations, transMat_precomp, viewmatrix,
+                             projmatrix, cam_pos, tan_fovx, tan_fovy, radii, g, grad_scratch, dL_dmean2D, dL_dnormal,
+                             dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat, dL_dsh, dL_dscale, dL_drot, st, debug);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Colour passes over one geometry / binning state (see the header)
+// ---------------------------------------------------------------------------------------------
+int surfel_pass_set_colors(int P, const float *colors, char *geometry_buffer, void *stream)
+{
+    if (P < 0) return fail("surfel_pass_set_colors", "bad sizes");
+    if (P == 0) return 0;
+    if (!colors || !geometry_buffer) return fail("surfel_pass_set_colors", "NULL required pointer");
+    GeomView g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    launch_set_record_colors(P, colors, g.rec, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_pass_set_colors", e);
+}
+
+int surfel_pass_render(int P, int width, int height, int64_t num_rendered, const float *background,
+                       char *geometry_buffer, char *binning_buffer, char *image_buffer, float *out_color,
+                       float *out_others, void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail("surfel_pass_render", "bad sizes");
+    if (!background || !image_buffer || !out_color || !out_others) return fail("surfel_pass_render", "NULL required pointer");
+    if (P > 0 && !geometry_buffer) return fail("surfel_pass_render", "NULL geometry");
+    if (num_rendered > 0 && !binning_buffer) return fail("surfel_pass_render", "NULL binning_buffer");
+    ImageView iv = carve_image(image_buffer, width, height);
+    GeomView g{};
+    BinView bv{};
+    if (P > 0) g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
+    return render_pass(width, height, background, g, iv, bv, out_color, out_others, st, debug);
+}
+
+int surfel_pass_backward_blend(int P, int width, int height, int64_t num_rendered, const float *background,
+                               char *geometry_buffer, char *binning_buffer, char *image_buffer, const float *dL_dpix,
+                               const float *dL_dothers, char *grad_scratch, int clear, void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail("surfel_pass_backward_blend", "bad sizes");
+    if (P == 0) return 0;
+    if (!background || !geometry_buffer || !image_buffer || !dL_dpix || !dL_dothers || !grad_scratch)
+        return fail("surfel_pass_backward_blend", "NULL required pointer");
+    if (num_rendered > 0 && !binning_buffer) return fail("surfel_pass_backward_blend", "NULL binning_buffer");
+    GeomView g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    ImageView iv = carve_image(image_buffer, width, height);
+    BinView bv{};
+    if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
+    return backward_blend(P, width, height, num_rendered, background, g, iv, bv, dL_dpix, dL_dothers, grad_scratch,
+                          clear != 0, st, debug);
+}
+
+int surfel_pass_take_color_grad(int P, char *grad_scratch, float *dL_dcolor, void *stream)
+{
+    if (P < 0) return fail("surfel_pass_take_color_grad", "bad sizes");
+    if (P == 0) return 0;
+    if (!grad_scratch) return fail("surfel_pass_take_color_grad", "NULL required pointer");
     char *gp = grad_scratch;
     float *gacc = carve<float>(gp, (size_t)P * GACC_FLOATS);
-    CK("grad scratch clear", cudaMemsetAsync(gacc, 0, (size_t)P * GACC_FLOATS * sizeof(float), st));
+    launch_take_color_grad(P, gacc, dL_dcolor, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_pass_take_color_grad", e);
+}
 
-    if (num_rendered > 0) {
-        RenderBwdArgs r;
-        r.W = width; r.H = height; r.gx = gx; r.gy = gy;
-        r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
-        r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
-        r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = gacc; r.subtile_cull = g_subtile_cull;
-        {
-            StageClock clk(st, 4);
-            launch_render_bwd(r, st);
-        }
-        STAGE("render backward");
-    }
-
-    PreprocessBwdArgs a;
-    a.P = P; a.D = D; a.M = M;
-    a.focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:388-389
-    a.focal_x = width / (2.0f * tan_fovx);
-    a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
-    a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
-    a.transMat_precomp = transMat_precomp; a.viewmatrix = viewmatrix; a.projmatrix = projmatrix; a.cam_pos = cam_pos;
-    a.radii = radii; a.clamped = g.clamped; a.rec = g.rec; a.gacc = gacc;
-    a.dL_dmean2D = dL_dmean2D; a.dL_dnormal = dL_dnormal; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
-    a.dL_dmean3D = dL_dmean3D; a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale;
-    a.dL_drot = dL_drot;
-    {
-        StageClock clk(st, 5);
-        launch_preprocess_bwd(a, st);
-    }
-    STAGE("preprocess backward");
-    return 0;
+int surfel_pass_backward_geometry(int P, int width, int height, const float *means3D, const float *scales,
+                                  const float *rotations, const float *transMat_precomp, const float *viewmatrix,
+                                  const float *projmatrix, const float *cam_pos, float tan_fovx, float tan_fovy,
+                                  const int *radii, char *geometry_buffer, char *grad_scratch, float *dL_dmean2D,
+                                  float *dL_dnormal, float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D,
+                                  float *dL_dtransMat, float *dL_dscale, float *dL_drot, void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const char *where = "surfel_pass_backward_geometry";
+    if (P < 0 || width <= 0 || height <= 0) return fail(where, "bad sizes");
+    if (P == 0) return 0;
+    if (!means3D || !viewmatrix || !projmatrix || !cam_pos || !radii || !geometry_buffer || !grad_scratch ||
+        !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dtransMat || !dL_dscale || !dL_drot)
+        return fail(where, "NULL required pointer");
+    if ((scales == nullptr) != (rotations == nullptr) || ((scales == nullptr) && !transMat_precomp))
+        return fail(where, "provide (scales, rotations) or transMat_precomp");
+    if (!aligned(dL_dscale, 8) || !aligned(dL_drot, 16) || (scales && (!aligned(scales, 8) || !aligned(rotations, 16))))
+        return fail(where, "scale/rotation buffers must be 8/16-byte aligned");
+    GeomView g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    return backward_geometry(P, 0, 0, width, height, means3D, nullptr, scales, rotations, transMat_precomp, viewmatrix,
+                             projmatrix, cam_pos, tan_fovx, tan_fovy, radii, g, grad_scratch, dL_dmean2D, dL_dnormal,
+                             dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat, nullptr, dL_dscale, dL_drot, st, debug);
 }
 
 int surfel_mark_visible(int P, const float *means3D, const float *viewmatrix, const float *projmatrix,

@@ -20,6 +20,9 @@ struct PreprocessFwdArgs {
     uint8_t *clamped;
 };
 void launch_preprocess_fwd(const PreprocessFwdArgs &a, cudaStream_t stream);
+// colour passes over one geometry state: rewrite the rgb words of the packed records / move the colour gradient out
+void launch_set_record_colors(int P, const float *colors, float *rec, cudaStream_t stream);
+void launch_take_color_grad(int P, float *gacc, float *dL_dcolor, cudaStream_t stream);
 void launch_mark_visible(int P, const float *means3D, const float *viewmatrix, unsigned char *present,
                          cudaStream_t stream);
 

@@ -383,6 +383,46 @@ void launch_mark_visible(int P, const float *means3D, const float *viewmatrix, u
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Colour passes over one geometry state: the blend kernels read a splat's colour
+// from words 15..17 of its packed record (common.cuh), so another pass with other precomputed colours
+// only has to rewrite those 12 bytes; its colour gradient is moved out of (and cleared in) words 12..14
+// of the gradient accumulator so that the geometry terms of all passes can keep summing there.
+// ---------------------------------------------------------------------------------------------
+__global__ void set_record_colors_kernel(const int P, const float *__restrict__ colors, float *__restrict__ rec)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    float *r = rec + (size_t)idx * REC_FLOATS;
+    r[15] = colors[3 * idx];
+    r[16] = colors[3 * idx + 1];
+    r[17] = colors[3 * idx + 2];
+}
+
+__global__ void take_color_grad_kernel(const int P, float *__restrict__ gacc, float *__restrict__ dL_dcolor)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    float *g = gacc + (size_t)idx * GACC_FLOATS;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (dL_dcolor) dL_dcolor[3 * idx + c] = g[12 + c];
+        g[12 + c] = 0.f;
+    }
+}
+
+void launch_set_record_colors(int P, const float *colors, float *rec, cudaStream_t stream)
+{
+    if (P == 0) return;
+    set_record_colors_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, colors, rec);
+}
+
+void launch_take_color_grad(int P, float *gacc, float *dL_dcolor, cudaStream_t stream)
+{
+    if (P == 0) return;
+    take_color_grad_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gacc, dL_dcolor);
+}
+
 // =============================================================================================
 // K8: backward preprocess.  One thread per Gaussian; consumes the gradient accumulator record
 // written by the backward render kernel and writes EVERY output element (zeros for culled
