@@ -297,6 +297,22 @@ SURFEL_API int surfel_loss_regulariser_backward(int width, int height, const flo
                                                 const float *surf_normal, const float *upstream,
                                                 float *d_rend_normal, float *d_surf_normal, float *d_rend_dist,
                                                 void *stream);
+/* Both halves and the combination of train.py:117-136 in three launches forward and two backward:
+ *   out5 = (loss, l1, ssim, Lnormal, Ldist),  loss = (1 - lambda_dssim) l1 + lambda_dssim (1 - ssim) + Lnormal + Ldist,
+ *   Lnormal = lambda_normal * mean(1 - <rend_normal, surf_normal>),  Ldist = lambda_dist * mean(rend_dist).
+ * g_out5 = 5 floats (device): the gradient of whatever the caller does with out5 (d/d loss = 1 for plain training). */
+SURFEL_API int surfel_loss_training_forward(int width, int height, const float *render, const float *rend_alpha,
+                                            const float *sky, const float *gt, const float *rend_normal,
+                                            const float *surf_normal, const float *rend_dist, float lambda_dssim,
+                                            float lambda_normal, float lambda_dist, float *deriv, char *scratch,
+                                            float *out5, void *stream);
+SURFEL_API int surfel_loss_training_backward(int width, int height, const float *render, const float *rend_alpha,
+                                             const float *sky, const float *gt, const float *rend_normal,
+                                             const float *surf_normal, const float *deriv, const float *g_out5,
+                                             float lambda_dssim, float lambda_normal, float lambda_dist,
+                                             float *d_render, float *d_rend_alpha, float *d_sky,
+                                             float *d_rend_normal, float *d_surf_normal, float *d_rend_dist,
+                                             void *stream);
 
 /*
  * ---------------------------------------------------------------------------------------------

@@ -54,6 +54,9 @@ SIGNATURES = {
     "surfel_loss_photometric_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_loss_regulariser_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_loss_regulariser_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_loss_training_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "surfel_loss_training_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp]),
     "surfel_adam_step": (_i, [_i, _vp, C.c_double, C.c_double, C.c_double, _vp]),
     "surfel_densification_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_sort_pairs": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -48,6 +48,21 @@ __device__ __forceinline__ void block_sum2(float &a, float &b, float (*red)[LOSS
 
 }  // namespace
 
+// How a backward kernel forms its two scalar weights from the upstream gradient vector on the device (no host
+// read-back): weight_k = sum_{j<n} c[k][j] * g[j].  The standalone entry points use the identity on 2 values; the fused
+// training loss mixes the 5 gradients of (loss, l1, ssim, Lnormal, Ldist) with the lambdas of train.py:117-136.
+struct UpstreamMix {
+    const float *g;
+    int n;
+    float c[2][5];
+    __device__ __forceinline__ float weight(const int k) const
+    {
+        float w = 0.f;
+        for (int j = 0; j < n; j++) w += c[k][j] * g[j];
+        return w;
+    }
+};
+
 __global__ void __launch_bounds__(LOSS_THREADS)
 loss_photometric_fwd_kernel(const LossImages im, const LossWindow win, float *__restrict__ deriv,
                             float *__restrict__ partials)
@@ -65,12 +80,12 @@ loss_photometric_fwd_kernel(const LossImages im, const LossWindow win, float *__
 
 __global__ void __launch_bounds__(LOSS_THREADS)
 loss_photometric_bwd_kernel(const LossImages im, const LossWindow win, const float *__restrict__ deriv,
-                            const float *__restrict__ upstream, float *__restrict__ d_render,
+                            const UpstreamMix upstream, float *__restrict__ d_render,
                             float *__restrict__ d_alpha, float *__restrict__ d_sky)
 {
     __shared__ LossBwdSmem s;
     const float inv_n = 1.0f / (3.0f * (float)im.W * (float)im.H);
-    const float wl = upstream[0] * inv_n, ws = upstream[1] * inv_n;
+    const float wl = upstream.weight(0) * inv_n, ws = upstream.weight(1) * inv_n;
     loss_bwd_tile(s, im, win, blockIdx.x * LT, blockIdx.y * LT, threadIdx.x, LOSS_THREADS, deriv, wl, ws, d_render,
                   d_alpha, d_sky);
 }
@@ -92,10 +107,10 @@ loss_regulariser_fwd_kernel(const float *__restrict__ rn, const float *__restric
 
 __global__ void __launch_bounds__(LOSS_THREADS)
 loss_regulariser_bwd_kernel(const float *__restrict__ rn, const float *__restrict__ sn, const size_t HW,
-                            const float *__restrict__ upstream, float *__restrict__ d_rn, float *__restrict__ d_sn,
+                            const UpstreamMix upstream, float *__restrict__ d_rn, float *__restrict__ d_sn,
                             float *__restrict__ d_dist)
 {
-    const float wn = upstream[0] / (float)HW, wd = upstream[1] / (float)HW;
+    const float wn = upstream.weight(0) / (float)HW, wd = upstream.weight(1) / (float)HW;
     regulariser_grads(rn, sn, HW, (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x, (size_t)gridDim.x * LOSS_THREADS, wn, wd,
                       d_rn, d_sn, d_dist);
 }
@@ -117,11 +132,46 @@ loss_finalize_kernel(const float *__restrict__ partials, const int nblocks, cons
     if (threadIdx.x < 2) out[threadIdx.x] = (float)(red[threadIdx.x][0] * scale);
 }
 
+// one CTA: both pairs of means and the combination of train.py:117-136 -> out5 = (loss, l1, ssim, Lnormal, Ldist)
+__global__ void __launch_bounds__(LOSS_THREADS)
+loss_training_finalize_kernel(const float *__restrict__ photo_partials, const int photo_blocks, const double photo_scale,
+                              const float *__restrict__ reg_partials, const int reg_blocks, const double reg_scale,
+                              const float lambda_dssim, const float lambda_normal, const float lambda_dist,
+                              float *__restrict__ out5)
+{
+    __shared__ double red[4][LOSS_THREADS];
+    for (int k = 0; k < 2; k++) {
+        red[k][threadIdx.x] = partial_column_sum(photo_partials, photo_blocks, k, threadIdx.x, LOSS_THREADS);
+        red[2 + k][threadIdx.x] = partial_column_sum(reg_partials, reg_blocks, k, threadIdx.x, LOSS_THREADS);
+    }
+    __syncthreads();
+    for (int o = LOSS_THREADS / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+            for (int k = 0; k < 4; k++) red[k][threadIdx.x] += red[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float l1 = (float)(red[0][0] * photo_scale), ssim = (float)(red[1][0] * photo_scale);
+        const float ln = lambda_normal * (float)(red[2][0] * reg_scale), ld = lambda_dist * (float)(red[3][0] * reg_scale);
+        out5[0] = (1.0f - lambda_dssim) * l1 + lambda_dssim * (1.0f - ssim) + ln + ld;
+        out5[1] = l1;
+        out5[2] = ssim;
+        out5[3] = ln;
+        out5[4] = ld;
+    }
+}
+
 constexpr int REG_BLOCKS = 148 * 4;   // regulariser kernels: grid-stride, a multiple of the SM count
 
 }  // namespace surfel
 
 using namespace surfel;
+
+static UpstreamMix identity_mix(const float *g)
+{
+    UpstreamMix m{g, 2, {{1.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 1.f, 0.f, 0.f, 0.f}}};
+    return m;
+}
 
 extern "C" {
 
@@ -132,8 +182,7 @@ size_t surfel_loss_scratch_bytes(int width, int height)
         return 0;
     }
     const size_t tiles = (size_t)((width + LT - 1) / LT) * ((height + LT - 1) / LT);
-    const size_t n = tiles > (size_t)REG_BLOCKS ? tiles : (size_t)REG_BLOCKS;
-    return 2 * n * sizeof(float) + 128;
+    return 2 * (tiles + (size_t)REG_BLOCKS) * sizeof(float) + 256;   // both partial arrays, each 128-byte aligned
 }
 
 int surfel_loss_photometric_forward(int width, int height, const float *render, const float *rend_alpha,
@@ -166,7 +215,7 @@ int surfel_loss_photometric_backward(int width, int height, const float *render,
     const LossImages im{render, rend_alpha, sky, gt, width, height};
     const dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT);
     loss_photometric_bwd_kernel<<<grid, LOSS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        im, make_loss_window(), deriv, upstream, d_render, d_rend_alpha, d_sky);
+        im, make_loss_window(), deriv, identity_mix(upstream), d_render, d_rend_alpha, d_sky);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : surfel_internal_fail(where, cudaGetErrorString(e));
 }
@@ -196,7 +245,57 @@ int surfel_loss_regulariser_backward(int width, int height, const float *rend_no
         !d_rend_dist)
         return surfel_internal_fail(where, "bad arguments");
     loss_regulariser_bwd_kernel<<<REG_BLOCKS, LOSS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        rend_normal, surf_normal, (size_t)width * height, upstream, d_rend_normal, d_surf_normal, d_rend_dist);
+        rend_normal, surf_normal, (size_t)width * height, identity_mix(upstream), d_rend_normal, d_surf_normal, d_rend_dist);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : surfel_internal_fail(where, cudaGetErrorString(e));
+}
+
+int surfel_loss_training_forward(int width, int height, const float *render, const float *rend_alpha, const float *sky,
+                                 const float *gt, const float *rend_normal, const float *surf_normal,
+                                 const float *rend_dist, float lambda_dssim, float lambda_normal, float lambda_dist,
+                                 float *deriv, char *scratch, float *out5, void *stream)
+{
+    const char *where = "surfel_loss_training_forward";
+    if (width <= 0 || height <= 0 || !render || !gt || !rend_normal || !surf_normal || !rend_dist || !scratch || !out5)
+        return surfel_internal_fail(where, "bad arguments");
+    if ((sky != nullptr) != (rend_alpha != nullptr)) return surfel_internal_fail(where, "sky and rend_alpha go together");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LossImages im{render, rend_alpha, sky, gt, width, height};
+    const dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT);
+    const int tiles = (int)(grid.x * grid.y);
+    const size_t HW = (size_t)width * height;
+    char *p = scratch;
+    float *photo_partials = carve<float>(p, 2 * (size_t)tiles);
+    float *reg_partials = carve<float>(p, 2 * (size_t)REG_BLOCKS);
+    loss_photometric_fwd_kernel<<<grid, LOSS_THREADS, 0, st>>>(im, make_loss_window(), deriv, photo_partials);
+    loss_regulariser_fwd_kernel<<<REG_BLOCKS, LOSS_THREADS, 0, st>>>(rend_normal, surf_normal, rend_dist, HW, reg_partials);
+    loss_training_finalize_kernel<<<1, LOSS_THREADS, 0, st>>>(photo_partials, tiles, 1.0 / (3.0 * (double)HW), reg_partials,
+                                                              REG_BLOCKS, 1.0 / (double)HW, lambda_dssim, lambda_normal,
+                                                              lambda_dist, out5);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : surfel_internal_fail(where, cudaGetErrorString(e));
+}
+
+int surfel_loss_training_backward(int width, int height, const float *render, const float *rend_alpha, const float *sky,
+                                  const float *gt, const float *rend_normal, const float *surf_normal, const float *deriv,
+                                  const float *g_out5, float lambda_dssim, float lambda_normal, float lambda_dist,
+                                  float *d_render, float *d_rend_alpha, float *d_sky, float *d_rend_normal,
+                                  float *d_surf_normal, float *d_rend_dist, void *stream)
+{
+    const char *where = "surfel_loss_training_backward";
+    if (width <= 0 || height <= 0 || !render || !gt || !rend_normal || !surf_normal || !deriv || !g_out5 || !d_render ||
+        !d_rend_normal || !d_surf_normal || !d_rend_dist)
+        return surfel_internal_fail(where, "bad arguments");
+    if ((sky != nullptr) != (rend_alpha != nullptr)) return surfel_internal_fail(where, "sky and rend_alpha go together");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LossImages im{render, rend_alpha, sky, gt, width, height};
+    const dim3 grid((width + LT - 1) / LT, (height + LT - 1) / LT);
+    // d loss / d l1 = 1 - lambda_dssim, d loss / d ssim = -lambda_dssim (train.py:117); Lnormal = lambda_normal * mean, ...
+    const UpstreamMix photo{g_out5, 5, {{1.0f - lambda_dssim, 1.f, 0.f, 0.f, 0.f}, {-lambda_dssim, 0.f, 1.f, 0.f, 0.f}}};
+    const UpstreamMix reg{g_out5, 5, {{lambda_normal, 0.f, 0.f, lambda_normal, 0.f}, {lambda_dist, 0.f, 0.f, 0.f, lambda_dist}}};
+    loss_photometric_bwd_kernel<<<grid, LOSS_THREADS, 0, st>>>(im, make_loss_window(), deriv, photo, d_render, d_rend_alpha, d_sky);
+    loss_regulariser_bwd_kernel<<<REG_BLOCKS, LOSS_THREADS, 0, st>>>(rend_normal, surf_normal, (size_t)width * height, reg,
+                                                                      d_rend_normal, d_surf_normal, d_rend_dist);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : surfel_internal_fail(where, cudaGetErrorString(e));
 }

@@ -127,15 +127,71 @@ def ssim(img1, img2, window_size=11, size_average=True):
     return l1_and_ssim(img1, img2)[1]
 
 
+class _TrainingLoss(torch.autograd.Function):
+    """(render, rend_alpha | None, sky | None, gt, rend_normal, surf_normal, rend_dist, lambdas) ->
+    tensor [5] = (loss, l1, ssim, Lnormal, Ldist) in three launches forward and two backward; the upstream gradient of
+    all five values is mixed with the lambdas on the device."""
+
+    @staticmethod
+    def forward(ctx, render, rend_alpha, sky, gt, rend_normal, surf_normal, rend_dist, lambda_dssim, lambda_normal,
+                lambda_dist):
+        render, gt = _image(render, "render", 3), _image(gt, "gt_image", 3)
+        rn, sn = _image(rend_normal, "rend_normal", 3), _image(surf_normal, "surf_normal", 3)
+        dist = _image(rend_dist, "rend_dist", 1)
+        if (sky is None) != (rend_alpha is None):
+            raise RuntimeError("sky and rend_alpha go together")
+        if sky is not None:
+            sky, rend_alpha = _image(sky, "sky_image", 3), _image(rend_alpha, "rend_alpha", 1)
+        shapes = [gt.shape, rn.shape, sn.shape] + ([sky.shape] if sky is not None else [])
+        planes = [dist.shape[1:]] + ([rend_alpha.shape[1:]] if sky is not None else [])
+        if any(x != render.shape for x in shapes) or any(x != render.shape[1:] for x in planes):
+            raise RuntimeError("image shapes differ")
+        if ctx.needs_input_grad[3]:
+            raise RuntimeError("gradients with respect to the ground-truth image are not supported")
+        _, H, W = render.shape
+        dev = render.device
+        need_grad = any(ctx.needs_input_grad[:7])
+        lam = (float(lambda_dssim), float(lambda_normal), float(lambda_dist))
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            deriv = torch.empty((9, H, W), dtype=torch.float32, device=dev) if need_grad else None
+            scratch = torch.empty(_lib.size(L.surfel_loss_scratch_bytes(W, H), "surfel_loss_scratch_bytes"),
+                                  dtype=torch.uint8, device=dev)
+            out5 = torch.empty(5, dtype=torch.float32, device=dev)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(L.surfel_loss_training_forward(W, H, _p(render), _p(rend_alpha), _p(sky), _p(gt), _p(rn), _p(sn),
+                                                      _p(dist), lam[0], lam[1], lam[2], _p(deriv), _p(scratch), _p(out5),
+                                                      st), "surfel_loss_training_forward")
+        ctx.save_for_backward(render, rend_alpha, sky, gt, rn, sn, deriv)
+        ctx.lam = lam
+        return out5
+
+    @staticmethod
+    def backward(ctx, g_out5):
+        render, rend_alpha, sky, gt, rn, sn, deriv = ctx.saved_tensors
+        _, H, W = render.shape
+        g = g_out5.contiguous().float()
+        need = ctx.needs_input_grad
+        d_render = torch.empty_like(render)
+        d_alpha = torch.empty_like(rend_alpha) if sky is not None and need[1] else None
+        d_sky = torch.empty_like(sky) if sky is not None and need[2] else None
+        d_rn, d_sn = torch.empty_like(rn), torch.empty_like(sn)
+        d_dist = torch.empty((1, H, W), dtype=torch.float32, device=render.device)
+        with torch.cuda.device(render.device):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().surfel_loss_training_backward(
+                W, H, _p(render), _p(rend_alpha), _p(sky), _p(gt), _p(rn), _p(sn), _p(deriv), _p(g), ctx.lam[0], ctx.lam[1],
+                ctx.lam[2], _p(d_render), _p(d_alpha), _p(d_sky), _p(d_rn), _p(d_sn), _p(d_dist), st),
+                "surfel_loss_training_backward")
+        return d_render, d_alpha, d_sky, None, d_rn, d_sn, d_dist, None, None, None
+
+
 def training_loss(render_pkg, sky_image, gt_image, lambda_dssim, lambda_normal=0.0, lambda_dist=0.0):
     """train.py:113-136: ``(loss, loss_dict)`` with the reference's keys ``l1, ssim, Lnormal, Ldist``.
     ``sky_image`` may be None (composite = render).  The shrink term (train.py:138-141) is a mean over the opacity
     parameters, not an image operation, and stays with the caller."""
     alpha = render_pkg["rend_alpha"] if sky_image is not None else None
-    Ll1, Lssim = l1_and_ssim(render_pkg["render"], gt_image, alpha, sky_image)
-    loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - Lssim)
-    reg = _Regulariser.apply(render_pkg["rend_normal"], render_pkg["surf_normal"], render_pkg["rend_dist"])
-    normal_loss = lambda_normal * reg[0]
-    dist_loss = lambda_dist * reg[1]
-    loss = loss + normal_loss + dist_loss
+    out5 = _TrainingLoss.apply(render_pkg["render"], alpha, sky_image, gt_image, render_pkg["rend_normal"],
+                               render_pkg["surf_normal"], render_pkg["rend_dist"], lambda_dssim, lambda_normal, lambda_dist)
+    loss, Ll1, Lssim, normal_loss, dist_loss = out5.unbind(0)
     return loss, {"l1": Ll1, "ssim": Lssim, "Lnormal": normal_loss, "Ldist": dist_loss}
