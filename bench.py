@@ -230,33 +230,53 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
     ev_comp = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
     out_host = [{}, {}]
+    trace = [] if os.environ.get("BENCH_E2E_TRACE") else None   # diagnostics: per-phase device timestamps on stderr
+
+    def mark(stream):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
 
     def one(i):
         k = i % 2
         step, leaves, m2, state = sets[k]
+        t = {}
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_comp[k])          # the previous step on this buffer set has consumed its inputs
+            if trace is not None:
+                t["in0"] = mark(s_in)
             for name in leaves:
                 leaves[name].data.copy_(pin[name], non_blocking=True)
             state["grads"][0].copy_(pin_g[0], non_blocking=True)
             state["grads"][1].copy_(pin_g[1], non_blocking=True)
             ev_in[k].record(s_in)
+            if trace is not None:
+                t["in1"] = mark(s_in)
         with torch.cuda.stream(s_comp):
             s_comp.wait_event(ev_in[k])
             s_comp.wait_event(ev_out[k])         # its previous results have left the device
+            if trace is not None:
+                t["c0"] = mark(s_comp)
             st = step()
             outs = {"color": st["color"], "allmap": st["allmap"], "radii": st["radii"], "g_means2D": m2.grad}
             outs.update({"g_" + name: v.grad for name, v in leaves.items()})
             for v in outs.values():
                 v.record_stream(s_out)
             ev_comp[k].record(s_comp)
+            if trace is not None:
+                t["c1"] = mark(s_comp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_comp[k])
+            if trace is not None:
+                t["out0"] = mark(s_out)
             for name, v in outs.items():
                 if name not in out_host[k]:
                     out_host[k][name] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
                 out_host[k][name].copy_(v.detach(), non_blocking=True)
             ev_out[k].record(s_out)
+            if trace is not None:
+                t["out1"] = mark(s_out)
+                trace.append(t)
 
     steps = max(4, args.steps)
     for i in range(2):
@@ -276,6 +296,9 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
     e1.record(cur)
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / steps
+    if trace:
+        for i, t in enumerate(trace[2:8]):   # the first timed steps, milliseconds since the start of the timed region
+            print("e2e trace step", i, {n: round(e0.elapsed_time(ev), 2) for n, ev in t.items()}, file=sys.stderr)
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

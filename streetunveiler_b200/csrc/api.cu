@@ -17,6 +17,7 @@ namespace {
 
 thread_local std::string g_err;
 int g_subtile_cull = 1;
+int g_bwd_variant = 0;
 
 // ---- optional per-stage device timing (bench.py roofline measurement) ----
 constexpr int N_STAGES = 6;
@@ -151,6 +152,40 @@ WindowView carve_window(char *base, int P, size_t cub_bytes)
     return w;
 }
 
+// ---- num_rendered read-back without the copy engine -------------------------------------------------
+// The reference reads R back with a blocking cudaMemcpy into pageable memory (rasterizer_impl.cu:282).  That 4-byte copy
+// is queued on the device-to-host DMA engine BEHIND whatever bulk transfer another stream has in flight -- in a pipelined
+// training loop the whole forward then waits for the previous step's results to finish leaving the device (measured: the
+// step time becomes compute + transfer instead of max(compute, transfer)).  Here a one-thread kernel stores the value
+// straight into a pinned, mapped host word (one lazily allocated slot per host thread, never freed), so the read-back
+// only waits for the kernels in front of it on its own stream.
+__global__ void publish_u32_kernel(const uint32_t *__restrict__ src, volatile uint32_t *__restrict__ dst_mapped)
+{
+    *dst_mapped = *src;
+    __threadfence_system();
+}
+
+cudaError_t read_back_u32(const uint32_t *dev_value, uint32_t *out, cudaStream_t st)
+{
+    thread_local uint32_t *slot = nullptr;
+    if (!slot) {
+        void *h = nullptr;
+        cudaError_t e = cudaHostAlloc(&h, 64, cudaHostAllocPortable | cudaHostAllocMapped);
+        if (e != cudaSuccess) return e;
+        slot = static_cast<uint32_t *>(h);
+    }
+    uint32_t *dptr = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&dptr), slot, 0);
+    if (e != cudaSuccess) return e;
+    publish_u32_kernel<<<1, 1, 0, st>>>(dev_value, dptr);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    *out = *static_cast<volatile uint32_t *>(slot);
+    return cudaSuccess;
+}
+
 bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 bool have_device()
@@ -175,6 +210,8 @@ int backward_blend(int P, int width, int height, int64_t num_rendered, const flo
         r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
         r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
         r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = gacc; r.subtile_cull = g_subtile_cull;
+        r.aux_flag = carve<int>(gp, 1);   // the 128 spare bytes behind the accumulator (surfel_grad_scratch_bytes)
+        r.variant = g_bwd_variant;
         {
             StageClock clk(st, 4);
             launch_render_bwd(r, st);
@@ -257,6 +294,10 @@ int surfel_set_option(const char *name, int value)
         g_subtile_cull = value;
         return 0;
     }
+    if (name && std::strcmp(name, "bwd_variant") == 0) {
+        g_bwd_variant = value;
+        return 0;
+    }
     if (name && std::strcmp(name, "time_stages") == 0) {  // (re)arms and clears the stage clocks
         g_time_stages = value;
         for (int i = 0; i < N_STAGES; i++) { g_stage_ms[i] = 0; g_stage_calls[i] = 0; }
@@ -292,7 +333,7 @@ size_t surfel_binning_bytes(int64_t num_rendered)
 size_t surfel_grad_scratch_bytes(int P)
 {
     if (P < 0) { fail("surfel_grad_scratch_bytes", "negative P"); return 0; }
-    return (size_t)(P > 0 ? P : 1) * GACC_FLOATS * sizeof(float) + 128;
+    return (size_t)(P > 0 ? P : 1) * GACC_FLOATS * sizeof(float) + 256;   // accumulator + one aligned flag word
 }
 
 int surfel_forward_prepare(int P, int D, int M, int width, int height, const float *means3D, const float *shs,
@@ -346,8 +387,7 @@ int surfel_forward_prepare(int P, int D, int M, int width, int height, const flo
     STAGE("depth order");
 
     uint32_t r32 = 0;
-    CK("num_rendered readback", cudaMemcpyAsync(&r32, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK("num_rendered readback", cudaStreamSynchronize(st));
+    CK("num_rendered readback", read_back_u32(g.offsets + (P - 1), &r32, st));
     *num_rendered = (int64_t)r32;
     return 0;
 }
@@ -629,8 +669,7 @@ int surfel_window_prepare(int P_total, int width, int height, int row_offset, in
                                       w.offsets, nullptr, w.cub_temp, w.cub_temp_bytes, st));
     STAGE("depth order");
     uint32_t r32 = 0;
-    CK("num_rendered readback", cudaMemcpyAsync(&r32, w.offsets + (P_total - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK("num_rendered readback", cudaStreamSynchronize(st));
+    CK("num_rendered readback", read_back_u32(w.offsets + (P_total - 1), &r32, st));
     *num_rendered = (int64_t)r32;
     return 0;
 }

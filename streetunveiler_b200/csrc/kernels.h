@@ -100,6 +100,8 @@ struct RenderBwdArgs {
     const float *dL_dpix, *dL_dothers;
     float *gacc;  // [P][GACC_FLOATS], zero-initialised by the caller of the launch
     int subtile_cull;
+    int *aux_flag = nullptr;  // one scratch word for the "any depth/normal/distortion gradient?" flag, or nullptr
+    int variant = 0;          // kernel selection, see launch_render_bwd ("bwd_variant" option)
 };
 void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream);
 

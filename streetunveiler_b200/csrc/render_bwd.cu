@@ -65,9 +65,27 @@ struct Butterfly {
     }
 };
 
-template <bool CULL>
-__global__ void __maxnreg__(96)
-render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
+// Depth / normal / median-depth / distortion upstream gradients are exactly zero for whole frames in practice
+// (train.py enables those losses late; BASELINE configs 2, 3, 5): aux_zero_scan_kernel finds out on the device and
+// the launcher queues BOTH specialisations of the blend kernel -- AUX = true (all recurrences, 96 registers) and
+// AUX = false (colour + alpha only: 14 fewer live values per pixel) -- each of which returns at once unless the flag
+// selects it.  No host round trip; the cost is one pass over six gradient planes and one empty launch.
+__global__ void __launch_bounds__(256) aux_zero_scan_kernel(const float *__restrict__ dL_dothers, const size_t HW,
+                                                            int *__restrict__ flag)
+{
+    bool any = false;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (size_t)gridDim.x * blockDim.x)
+        any |= dL_dothers[p] != 0.f || dL_dothers[2 * HW + p] != 0.f || dL_dothers[3 * HW + p] != 0.f ||
+               dL_dothers[4 * HW + p] != 0.f || dL_dothers[5 * HW + p] != 0.f || dL_dothers[6 * HW + p] != 0.f;
+    if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;   // benign race: every writer stores 1
+}
+
+// CULL: sub-tile culling on.  AUX: see above.  REGS: register cap (occupancy).  SPARSE: when at most two pixels of
+// the warp contribute to an instance, those lanes add their values directly instead of running the butterfly.
+template <bool CULL, bool AUX, int REGS, bool SPARSE>
+__global__ void __maxnreg__(REGS)
+render_bwd_kernel(const int *__restrict__ aux_flag,
+                  const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
                   const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
                   const float *__restrict__ bg, const float *__restrict__ final_Ts,
@@ -77,6 +95,8 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileRing<BWD_STAGES> &ring = *reinterpret_cast<TileRing<BWD_STAGES> *>(smem_raw);
+
+    if (aux_flag && (*aux_flag != 0) != AUX) return;   // the other specialisation handles this frame
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -115,13 +135,15 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
     float dL_dreg = 0.f, dL_ddepth = 0.f, dL_daccum = 0.f, dL_dmedian_depth = 0.f;
     float dL_dnormal2D[3] = {0.f, 0.f, 0.f};
     if (inside) {
-        dL_ddepth = dL_dothers[pix_id];
         dL_daccum = dL_dothers[HW + pix_id];
-        dL_dnormal2D[0] = dL_dothers[2 * HW + pix_id];
-        dL_dnormal2D[1] = dL_dothers[3 * HW + pix_id];
-        dL_dnormal2D[2] = dL_dothers[4 * HW + pix_id];
-        dL_dmedian_depth = dL_dothers[5 * HW + pix_id];
-        dL_dreg = dL_dothers[6 * HW + pix_id];
+        if (AUX) {
+            dL_ddepth = dL_dothers[pix_id];
+            dL_dnormal2D[0] = dL_dothers[2 * HW + pix_id];
+            dL_dnormal2D[1] = dL_dothers[3 * HW + pix_id];
+            dL_dnormal2D[2] = dL_dothers[4 * HW + pix_id];
+            dL_dmedian_depth = dL_dothers[5 * HW + pix_id];
+            dL_dreg = dL_dothers[6 * HW + pix_id];
+        }
         dL_dpixel[0] = dL_dpixels[pix_id];
         dL_dpixel[1] = dL_dpixels[HW + pix_id];
         dL_dpixel[2] = dL_dpixels[2 * HW + pix_id];
@@ -143,11 +165,10 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
     const int my_slot = Butterfly<NV, 4>::slot(lane, 0, NV);
     const int my_slot15 = Butterfly<15, 4>::slot(lane, 0, 15);  // without the three normal gradients
 
-    // Depth / normal / median-depth / distortion upstream gradients are exactly zero for whole frames in
-    // practice (train.py enables those losses late): skip their recurrences when no pixel of the warp has any.
-    const bool aux_any = __any_sync(0xffffffffu, dL_ddepth != 0.f || dL_dreg != 0.f || dL_dmedian_depth != 0.f ||
-                                                     dL_dnormal2D[0] != 0.f || dL_dnormal2D[1] != 0.f ||
-                                                     dL_dnormal2D[2] != 0.f);
+    // ... and within a frame that has some, skip their recurrences for warps none of whose pixels has any.
+    const bool aux_any = AUX && __any_sync(0xffffffffu, dL_ddepth != 0.f || dL_dreg != 0.f || dL_dmedian_depth != 0.f ||
+                                                            dL_dnormal2D[0] != 0.f || dL_dnormal2D[1] != 0.f ||
+                                                            dL_dnormal2D[2] != 0.f);
 
     int stage = 0;
     uint32_t phase = 0;
@@ -287,9 +308,22 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
                         }
                     }
                 }
-                if (__any_sync(0xffffffffu, valid)) {
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                if (vmask) {
                     float *dst = gacc + (size_t)ring.id[stage][jj] * GACC_FLOATS;
-                    if (aux_any) {
+                    if (SPARSE && __popc(vmask) <= 2) {
+                        // one or two contributing pixels: 15-18 predicated reductions cost less than the butterfly
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 15; i++)
+                                if (v[i] != 0.f) red_add_f32(dst + i, v[i]);
+                            if (aux_any) {
+#pragma unroll
+                                for (int i = 15; i < NV; i++)
+                                    if (v[i] != 0.f) red_add_f32(dst + i, v[i]);
+                            }
+                        }
+                    } else if (aux_any) {
                         Butterfly<NV, 4>::run(v, lane);
                         if (my_slot >= 0) red_add_f32(dst + my_slot, v[0]);
                     } else {  // v[15..17] (normal gradients) are identically zero: 16 shuffles instead of 20
@@ -305,23 +339,37 @@ render_bwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
     }
 }
 
+template <bool CULL, bool AUX, int REGS, bool SPARSE>
+static void launch_one(const RenderBwdArgs &a, const int tiles, const int *flag, cudaStream_t stream)
+{
+    auto k = render_bwd_kernel<CULL, AUX, REGS, SPARSE>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<BWD_STAGES>));  // per device, cheap
+    k<<<tiles, TILE_THREADS, sizeof(TileRing<BWD_STAGES>), stream>>>(flag, a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list,
+                                                                      a.rec, a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
+                                                                      a.dL_dpix, a.dL_dothers, a.gacc);
+}
+
 void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
 {
     const int rows = a.gy > a.row_offset ? (a.gy - a.row_offset + a.row_stride - 1) / a.row_stride : 0;
     const int tiles = a.gx * rows;
     if (tiles == 0) return;
-    {  // per device and cheap: opt in to more than 48 KB of dynamic shared memory
-        cudaFuncSetAttribute(render_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<BWD_STAGES>));
-        cudaFuncSetAttribute(render_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<BWD_STAGES>));
+    if (!a.subtile_cull) {   // debugging aid only
+        launch_one<false, true, 96, false>(a, tiles, nullptr, stream);
+        return;
     }
-    if (a.subtile_cull)
-        render_bwd_kernel<true><<<tiles, TILE_THREADS, sizeof(TileRing<BWD_STAGES>), stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec, a.bg,
-                                                           a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
-                                                           a.dL_dothers, a.gacc);
-    else
-        render_bwd_kernel<false><<<tiles, TILE_THREADS, sizeof(TileRing<BWD_STAGES>), stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec, a.bg,
-                                                            a.final_T, a.n_contrib, a.tile_max_contrib, a.dL_dpix,
-                                                            a.dL_dothers, a.gacc);
+    if (a.aux_flag == nullptr || a.variant == 0) {   // no scratch word for the flag (sharded window path) or variant 0
+        launch_one<true, true, 96, false>(a, tiles, nullptr, stream);
+        return;
+    }
+    cudaMemsetAsync(a.aux_flag, 0, sizeof(int), stream);
+    aux_zero_scan_kernel<<<148 * 4, 256, 0, stream>>>(a.dL_dothers, (size_t)a.W * a.H, a.aux_flag);
+    switch (a.variant) {
+    case 1:  launch_one<true, false, 96, false>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96, false>(a, tiles, a.aux_flag, stream); break;
+    case 2:  launch_one<true, false, 72, false>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96, false>(a, tiles, a.aux_flag, stream); break;
+    case 3:  launch_one<true, false, 96, true>(a, tiles, a.aux_flag, stream);  launch_one<true, true, 96, true>(a, tiles, a.aux_flag, stream);  break;
+    default: launch_one<true, false, 72, true>(a, tiles, a.aux_flag, stream);  launch_one<true, true, 96, true>(a, tiles, a.aux_flag, stream);  break;
+    }
 }
 
 }  // namespace surfel

@@ -261,3 +261,29 @@ def test_subtile_culling_is_exact_on_adversarial_scenes(seed):
         assert np.array_equal(a["radii"], r["radii"]) and a["num_rendered"] == r["num_rendered"]
         for k, v in hz.compare(a, r).items():
             assert v <= TOL, (k, v)
+
+
+@pytest.mark.parametrize("mode", ["color_alpha", "all", "sparse_aux"])
+def test_backward_kernel_variants_agree(mode):
+    """The backward blend has several specialisations (bwd_variant option: device-side choice between the full kernel and
+    the colour+alpha-only one, a tighter register cap, direct reductions for 1-2 contributing pixels).  Every variant
+    must give the gradients of variant 0 on frames without, with, and with a few depth/normal/distortion gradients."""
+    from streetunveiler_b200 import _lib
+    cam = syn.cam_tilted(640, 400, 520.0)
+    sc = syn.street_scene(60_000, 9, 3)
+    sc["scales"] = (sc["scales"] * 2).contiguous()
+    grads = syn.upstream_grads(cam.width, cam.height, "all" if mode == "all" else "color_alpha", seed=11)
+    if mode == "sparse_aux":           # a single pixel carries a distortion gradient: the flag must still say "aux"
+        grads[1][6, 123, 321] = 1e-3
+    ref = None
+    try:
+        for variant in range(5):
+            _lib.set_option("bwd_variant", variant)
+            out = hz.run_ours(sc, cam, grads=grads)
+            if ref is None:
+                ref = out
+                continue
+            for k in ("g_means3D", "g_means2D", "g_opacities", "g_shs", "g_scales", "g_rotations"):
+                assert hz.rel_err(out[k], ref[k]) <= 1e-5, (variant, k, hz.rel_err(out[k], ref[k]))
+    finally:
+        _lib.set_option("bwd_variant", 0)
