@@ -218,7 +218,8 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
     """Same metric through the operator with HOST buffers: every step copies all inputs (parameters and
     upstream gradients) from pinned host memory to the device, runs fwd+bwd, and copies every output and
     gradient back to pinned host memory.  Steps are software-pipelined over two device buffer sets and
-    three streams (H2D of step i+1 | compute of step i | D2H of step i-1), PCIe being full duplex."""
+    three streams (H2D of step i+1 | compute of step i | D2H of step i-1), PCIe being full duplex; the upload
+    of step i+1 is queued before step i's kernels so that it does not wait for the host's num_rendered read-back."""
     pin = {k: v.pin_memory() for k, v in wl.host.items() if isinstance(v, torch.Tensor)}
     pin_g = [g.pin_memory() for g in wl.grads_host]
     h2d = sum(v.numel() * v.element_size() for v in pin.values()) + sum(g.numel() * 4 for g in pin_g)
@@ -237,12 +238,13 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
         e.record(stream)
         return e
 
-    def one(i):
+    def upload(i):
+        """H2D of step i's inputs into buffer set i % 2 (waits until step i-2 has consumed that set)."""
         k = i % 2
-        step, leaves, m2, state = sets[k]
+        _, leaves, _, state = sets[k]
         t = {}
         with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_comp[k])          # the previous step on this buffer set has consumed its inputs
+            s_in.wait_event(ev_comp[k])
             if trace is not None:
                 t["in0"] = mark(s_in)
             for name in leaves:
@@ -252,6 +254,17 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
             ev_in[k].record(s_in)
             if trace is not None:
                 t["in1"] = mark(s_in)
+        return t
+
+    pending = {}
+
+    def one(i):
+        # step i: its inputs were queued by the previous call (or the prologue); queue the NEXT step's upload first, so
+        # that the copy engine is busy while the host is inside this step's forward (which waits for num_rendered)
+        k = i % 2
+        step, leaves, m2, state = sets[k]
+        t = pending.pop(i) if i in pending else upload(i)
+        pending[i + 1] = upload(i + 1)
         with torch.cuda.stream(s_comp):
             s_comp.wait_event(ev_in[k])
             s_comp.wait_event(ev_out[k])         # its previous results have left the device
@@ -281,6 +294,8 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
     steps = max(4, args.steps)
     for i in range(2):
         one(i)
+    # every timed step uploads exactly one set of inputs (the one for the step after it) and downloads one set of
+    # results; the upload queued by the last warm-up step belongs to the first timed step
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize(device)
@@ -289,7 +304,7 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
     e0.record(cur)
     for s_ in (s_in, s_out):
         s_.wait_stream(cur)
-    for i in range(steps):
+    for i in range(2, steps + 2):
         one(i)
     for s_ in (s_in, s_out):
         cur.wait_stream(s_)
@@ -297,8 +312,11 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / steps
     if trace:
-        for i, t in enumerate(trace[2:8]):   # the first timed steps, milliseconds since the start of the timed region
-            print("e2e trace step", i, {n: round(e0.elapsed_time(ev), 2) for n, ev in t.items()}, file=sys.stderr)
+        for i, t in enumerate(trace[3:9]):   # early timed steps, milliseconds since the start of the timed region
+            try:
+                print("e2e trace step", i + 1, {n: round(e0.elapsed_time(ev), 2) for n, ev in t.items()}, file=sys.stderr)
+            except Exception as exc:   # diagnostics only
+                print("e2e trace unavailable:", exc, file=sys.stderr)
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

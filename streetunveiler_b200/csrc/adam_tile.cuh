@@ -38,6 +38,35 @@ struct AdamLaunch {
     float eps;
 };
 
+// IEEE-rounded sqrtf / division that never leave the hardware fast path.  nvcc's sqrtf(x) branches to a software
+// routine for x == 0 and x < 2^-101, and a / b does for zero, denormal or extreme-exponent operands.  In this workload
+// those are the COMMON case, not the corner case: a Gaussian outside the current view has an exactly zero gradient,
+// its second moment is zero or decays towards the denormals, and its first moment shrinks by 0.9 per step -- measured
+// inside a training iteration the update kernel ran 2x slower than on dense random gradients because of it.  Scaling
+// by an even power of two is exact and commutes with round-to-nearest as long as the result is a normal number, so
+// the values are bit-identical to the plain expressions (a denormal quotient may differ in its last bit).
+__host__ __device__ inline float sqrt_fast_path(const float v)   // v >= 0
+{
+    const bool tiny = v < 1.0e-30f;
+    float s = tiny ? v * 18446744073709551616.0f : v;   // 2^64
+    const bool zero = s == 0.f;
+    s = zero ? 1.0f : s;
+    float r = sqrtf(s);
+    r = tiny ? r * 2.3283064365386963e-10f : r;         // 2^-32
+    return zero ? 0.f : r;
+}
+
+__host__ __device__ inline float div_fast_path(const float a, const float b)   // b: a normal number of moderate size
+{
+    const bool tiny = fabsf(a) < 1.0e-18f;
+    float s = tiny ? a * 18446744073709551616.0f : a;
+    const bool zero = s == 0.f;
+    s = zero ? 1.0f : s;
+    float q = s / b;
+    q = tiny ? q * 5.421010862427522e-20f : q;          // 2^-64
+    return zero ? 0.f : q;
+}
+
 // torch's arithmetic, in its order: lerp (|w| < 0.5 branch), mul, addcmul, sqrt / bc2_sqrt + eps, addcdiv
 __host__ __device__ inline void adam_element(float &p, const float g, float &m, float &v, const AdamLaunch &L,
                                              const AdamGroup &G)
@@ -45,8 +74,8 @@ __host__ __device__ inline void adam_element(float &p, const float g, float &m, 
     m = m + L.w1 * (g - m);
     v = v * L.beta2;
     v = v + (L.w2 * g) * g;
-    const float denom = sqrtf(v) / G.bc2_sqrt + L.eps;
-    p = p + G.step_size * (m / denom);
+    const float denom = div_fast_path(sqrt_fast_path(v), G.bc2_sqrt) + L.eps;
+    p = p + G.step_size * div_fast_path(m, denom);
 }
 
 // which group does chunk `c` belong to (groups are few: linear scan)

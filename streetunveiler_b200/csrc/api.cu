@@ -17,7 +17,7 @@ namespace {
 
 thread_local std::string g_err;
 int g_subtile_cull = 1;
-int g_bwd_variant = 0;
+int g_bwd_variant = 1;  // see launch_render_bwd
 
 // ---- optional per-stage device timing (bench.py roofline measurement) ----
 constexpr int N_STAGES = 6;

@@ -80,9 +80,10 @@ __global__ void __launch_bounds__(256) aux_zero_scan_kernel(const float *__restr
     if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;   // benign race: every writer stores 1
 }
 
-// CULL: sub-tile culling on.  AUX: see above.  REGS: register cap (occupancy).  SPARSE: when at most two pixels of
-// the warp contribute to an instance, those lanes add their values directly instead of running the butterfly.
-template <bool CULL, bool AUX, int REGS, bool SPARSE>
+// CULL: sub-tile culling on.  AUX: see above.  REGS: register cap -- 72 registers put three 9-warp CTAs on an SM instead
+// of two (the kernel is issue-bound with few resident warps: measured -20 % for AUX = false despite ~70 B of spills).
+// (Tried and dropped: direct per-lane reductions when only 1-2 pixels of a warp contribute -- slower than the butterfly.)
+template <bool CULL, bool AUX, int REGS>
 __global__ void __maxnreg__(REGS)
 render_bwd_kernel(const int *__restrict__ aux_flag,
                   const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
@@ -308,22 +309,9 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
                         }
                     }
                 }
-                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-                if (vmask) {
+                if (__any_sync(0xffffffffu, valid)) {
                     float *dst = gacc + (size_t)ring.id[stage][jj] * GACC_FLOATS;
-                    if (SPARSE && __popc(vmask) <= 2) {
-                        // one or two contributing pixels: 15-18 predicated reductions cost less than the butterfly
-                        if (valid) {
-#pragma unroll
-                            for (int i = 0; i < 15; i++)
-                                if (v[i] != 0.f) red_add_f32(dst + i, v[i]);
-                            if (aux_any) {
-#pragma unroll
-                                for (int i = 15; i < NV; i++)
-                                    if (v[i] != 0.f) red_add_f32(dst + i, v[i]);
-                            }
-                        }
-                    } else if (aux_any) {
+                    if (aux_any) {
                         Butterfly<NV, 4>::run(v, lane);
                         if (my_slot >= 0) red_add_f32(dst + my_slot, v[0]);
                     } else {  // v[15..17] (normal gradients) are identically zero: 16 shuffles instead of 20
@@ -339,10 +327,10 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
     }
 }
 
-template <bool CULL, bool AUX, int REGS, bool SPARSE>
+template <bool CULL, bool AUX, int REGS>
 static void launch_one(const RenderBwdArgs &a, const int tiles, const int *flag, cudaStream_t stream)
 {
-    auto k = render_bwd_kernel<CULL, AUX, REGS, SPARSE>;
+    auto k = render_bwd_kernel<CULL, AUX, REGS>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<BWD_STAGES>));  // per device, cheap
     k<<<tiles, TILE_THREADS, sizeof(TileRing<BWD_STAGES>), stream>>>(flag, a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list,
                                                                       a.rec, a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
@@ -355,20 +343,20 @@ void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
     const int tiles = a.gx * rows;
     if (tiles == 0) return;
     if (!a.subtile_cull) {   // debugging aid only
-        launch_one<false, true, 96, false>(a, tiles, nullptr, stream);
+        launch_one<false, true, 96>(a, tiles, nullptr, stream);
         return;
     }
     if (a.aux_flag == nullptr || a.variant == 0) {   // no scratch word for the flag (sharded window path) or variant 0
-        launch_one<true, true, 96, false>(a, tiles, nullptr, stream);
+        launch_one<true, true, 96>(a, tiles, nullptr, stream);
         return;
     }
     cudaMemsetAsync(a.aux_flag, 0, sizeof(int), stream);
     aux_zero_scan_kernel<<<148 * 4, 256, 0, stream>>>(a.dL_dothers, (size_t)a.W * a.H, a.aux_flag);
-    switch (a.variant) {
-    case 1:  launch_one<true, false, 96, false>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96, false>(a, tiles, a.aux_flag, stream); break;
-    case 2:  launch_one<true, false, 72, false>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96, false>(a, tiles, a.aux_flag, stream); break;
-    case 3:  launch_one<true, false, 96, true>(a, tiles, a.aux_flag, stream);  launch_one<true, true, 96, true>(a, tiles, a.aux_flag, stream);  break;
-    default: launch_one<true, false, 72, true>(a, tiles, a.aux_flag, stream);  launch_one<true, true, 96, true>(a, tiles, a.aux_flag, stream);  break;
+    switch (a.variant) {   // 1 is the default (api.cu); the others are kept for the occupancy experiment in tools/bench_variants.py
+    case 2:  launch_one<true, false, 72>(a, tiles, a.aux_flag, stream); launch_one<true, true, 72>(a, tiles, a.aux_flag, stream); break;
+    case 3:  launch_one<true, false, 56>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96>(a, tiles, a.aux_flag, stream); break;
+    case 4:  launch_one<true, false, 96>(a, tiles, a.aux_flag, stream); launch_one<true, true, 80>(a, tiles, a.aux_flag, stream); break;
+    default: launch_one<true, false, 72>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96>(a, tiles, a.aux_flag, stream); break;
     }
 }
 
