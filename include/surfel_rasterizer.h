@@ -263,6 +263,29 @@ SURFEL_API int surfel_pass_backward_geometry(int P, int width, int height, const
                                              int debug);
 
 /*
+ * Class-probability pass: ALL classes of render_semantic in one traversal of the lists.  The reference renders class
+ * probabilities as one-hot "colours", three classes per rasterizer call (gaussian_renderer/__init__.py:417-446).  With a
+ * per-Gaussian label instead (labels [P] int32; a label outside [0, n_classes) contributes to no class) one blend pass
+ * accumulates up to 8 class channels -- bit-identical to the one-hot formulation, since 1 * w and 0 * w are exact --
+ * and one backward blend returns the geometry gradients of all of them.  Sequence:
+ *     surfel_forward_prepare (any colour source; colours are not used)  ->  surfel_forward_bin
+ *     surfel_classes_set_labels  ->  surfel_classes_render (background [n_classes] -> out_probs [n_classes,H,W])
+ *     backward: surfel_classes_set_labels; surfel_classes_backward_blend (dL_dprobs [n_classes,H,W]);
+ *               surfel_pass_backward_geometry
+ */
+SURFEL_API int surfel_forward_bin(int P, int width, int height, int64_t num_rendered, const int *radii,
+                                  char *geometry_buffer, char *binning_buffer, char *image_buffer, void *stream,
+                                  int debug);
+SURFEL_API int surfel_classes_set_labels(int P, const int *labels, char *geometry_buffer, void *stream);
+SURFEL_API int surfel_classes_render(int P, int width, int height, int64_t num_rendered, int n_classes,
+                                     const float *background, char *geometry_buffer, char *binning_buffer,
+                                     char *image_buffer, float *out_probs, void *stream, int debug);
+SURFEL_API int surfel_classes_backward_blend(int P, int width, int height, int64_t num_rendered, int n_classes,
+                                             const float *background, char *geometry_buffer, char *binning_buffer,
+                                             char *image_buffer, const float *dL_dprobs, char *grad_scratch, int clear,
+                                             void *stream, int debug);
+
+/*
  * ---------------------------------------------------------------------------------------------
  * Fused training-loss block (reference: utils/loss_utils.py:17-64 l1_loss / ssim and
  * train.py:113-136, ~60 PyTorch kernels per iteration).  All images are dense fp32 [C,H,W] device arrays.

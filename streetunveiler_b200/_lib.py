@@ -49,6 +49,10 @@ SIGNATURES = {
     "surfel_pass_take_color_grad": (_i, [_i, _vp, _vp, _vp]),
     "surfel_pass_backward_geometry": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "surfel_forward_bin": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i]),
+    "surfel_classes_set_labels": (_i, [_i, _vp, _vp, _vp]),
+    "surfel_classes_render": (_i, [_i, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "surfel_classes_backward_blend": (_i, [_i, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i]),
     "surfel_loss_scratch_bytes": (C.c_size_t, [_i, _i]),
     "surfel_loss_photometric_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_loss_photometric_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

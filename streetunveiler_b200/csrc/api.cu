@@ -17,7 +17,7 @@ namespace {
 
 thread_local std::string g_err;
 int g_subtile_cull = 1;
-int g_bwd_variant = 1;  // see launch_render_bwd
+int g_bwd_variant = 2;  // see launch_render_bwd
 
 // ---- optional per-stage device timing (bench.py roofline measurement) ----
 constexpr int N_STAGES = 6;
@@ -198,7 +198,7 @@ bool have_device()
 // K7 into the per-Gaussian gradient accumulator (optionally cleared first) ...
 int backward_blend(int P, int width, int height, int64_t num_rendered, const float *background, const GeomView &g,
                    const ImageView &iv, const BinView &bv, const float *dL_dpix, const float *dL_dothers,
-                   char *grad_scratch, bool clear, cudaStream_t st, int debug)
+                   char *grad_scratch, bool clear, cudaStream_t st, int debug, int n_classes = 0)
 {
     char *gp = grad_scratch;
     float *gacc = carve<float>(gp, (size_t)P * GACC_FLOATS);
@@ -212,6 +212,7 @@ int backward_blend(int P, int width, int height, int64_t num_rendered, const flo
         r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = gacc; r.subtile_cull = g_subtile_cull;
         r.aux_flag = carve<int>(gp, 1);   // the 128 spare bytes behind the accumulator (surfel_grad_scratch_bytes)
         r.variant = g_bwd_variant;
+        r.n_classes = n_classes;
         {
             StageClock clk(st, 4);
             launch_render_bwd(r, st);
@@ -250,11 +251,26 @@ int backward_geometry(int P, int D, int M, int width, int height, const float *m
     return 0;
 }
 
+// K3-K5: emit (tile, id) pairs in depth order, stable-sort by tile, per-tile ranges, launch order
+int bin_stage(int P, int width, int height, int64_t num_rendered, const int *radii, const GeomView &g, const ImageView &iv,
+              const BinView &bv, cudaStream_t st, int debug)
+{
+    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    StageClock clk_bin(st, 2);
+    CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, 0, 1, g.rec, radii, g.idx_sorted, g.offsets,
+                                        bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted, bv.point_list, iv.ranges,
+                                        iv.tile_order, bv.cub_temp, bv.cub_temp_bytes, st));
+    clk_bin.stop();
+    STAGE("tile binning");
+    return 0;
+}
+
 // K6 over an existing binning state
 int render_pass(int width, int height, const float *background, const GeomView &g, const ImageView &iv,
-                const BinView &bv, float *out_color, float *out_others, cudaStream_t st, int debug)
+                const BinView &bv, float *out_color, float *out_others, cudaStream_t st, int debug, int n_classes = 0)
 {
     RenderFwdArgs r;
+    r.n_classes = n_classes;
     r.W = width; r.H = height;
     r.gx = (width + TILE_X - 1) / TILE_X; r.gy = (height + TILE_Y - 1) / TILE_Y;
     r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = g.rec; r.bg = background;
@@ -403,7 +419,6 @@ int surfel_forward_render(int P, int width, int height, int64_t num_rendered, co
     if (P > 0 && (!radii || !geometry_buffer)) return fail("surfel_forward_render", "NULL geometry");
     if (num_rendered > 0 && !binning_buffer) return fail("surfel_forward_render", "NULL binning_buffer");
 
-    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
     ImageView iv = carve_image(image_buffer, width, height);
     GeomView g{};
     BinView bv{};
@@ -412,13 +427,7 @@ int surfel_forward_render(int P, int width, int height, int64_t num_rendered, co
         const size_t cub = tile_sort_temp_bytes(num_rendered);
         bv = carve_bin(binning_buffer, num_rendered, cub);
     }
-    StageClock clk_bin(st, 2);
-    CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, 0, 1, g.rec, radii, g.idx_sorted, g.offsets,
-                                        bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted, bv.point_list, iv.ranges,
-                                        iv.tile_order, bv.cub_temp, bv.cub_temp_bytes, st));
-    clk_bin.stop();
-    STAGE("tile binning");
-
+    if (int rc = bin_stage(P, width, height, num_rendered, radii, g, iv, bv, st, debug)) return rc;
     return render_pass(width, height, background, g, iv, bv, out_color, out_others, st, debug);
 }
 
@@ -542,6 +551,74 @@ int surfel_pass_backward_geometry(int P, int width, int height, const float *mea
     return backward_geometry(P, 0, 0, width, height, means3D, nullptr, scales, rotations, transMat_precomp, viewmatrix,
                              projmatrix, cam_pos, tan_fovx, tan_fovy, radii, g, grad_scratch, dL_dmean2D, dL_dnormal,
                              dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat, nullptr, dL_dscale, dL_drot, st, debug);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Class-probability pass (see the header)
+// ---------------------------------------------------------------------------------------------
+int surfel_forward_bin(int P, int width, int height, int64_t num_rendered, const int *radii, char *geometry_buffer,
+                       char *binning_buffer, char *image_buffer, void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail("surfel_forward_bin", "bad sizes");
+    if (!image_buffer) return fail("surfel_forward_bin", "NULL required pointer");
+    if (P > 0 && (!radii || !geometry_buffer)) return fail("surfel_forward_bin", "NULL geometry");
+    if (num_rendered > 0 && !binning_buffer) return fail("surfel_forward_bin", "NULL binning_buffer");
+    ImageView iv = carve_image(image_buffer, width, height);
+    GeomView g{};
+    BinView bv{};
+    if (P > 0) g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
+    return bin_stage(P, width, height, num_rendered, radii, g, iv, bv, st, debug);
+}
+
+int surfel_classes_set_labels(int P, const int *labels, char *geometry_buffer, void *stream)
+{
+    if (P < 0) return fail("surfel_classes_set_labels", "bad sizes");
+    if (P == 0) return 0;
+    if (!labels || !geometry_buffer) return fail("surfel_classes_set_labels", "NULL required pointer");
+    GeomView g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    launch_set_record_labels(P, labels, g.rec, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_classes_set_labels", e);
+}
+
+int surfel_classes_render(int P, int width, int height, int64_t num_rendered, int n_classes, const float *background,
+                          char *geometry_buffer, char *binning_buffer, char *image_buffer, float *out_probs,
+                          void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail("surfel_classes_render", "bad sizes");
+    if (n_classes < 1 || n_classes > MAX_CLASSES) return fail("surfel_classes_render", "between 1 and 8 classes per pass");
+    if (!background || !image_buffer || !out_probs) return fail("surfel_classes_render", "NULL required pointer");
+    if (P > 0 && !geometry_buffer) return fail("surfel_classes_render", "NULL geometry");
+    if (num_rendered > 0 && !binning_buffer) return fail("surfel_classes_render", "NULL binning_buffer");
+    ImageView iv = carve_image(image_buffer, width, height);
+    GeomView g{};
+    BinView bv{};
+    if (P > 0) g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
+    return render_pass(width, height, background, g, iv, bv, out_probs, nullptr, st, debug, n_classes);
+}
+
+int surfel_classes_backward_blend(int P, int width, int height, int64_t num_rendered, int n_classes,
+                                  const float *background, char *geometry_buffer, char *binning_buffer,
+                                  char *image_buffer, const float *dL_dprobs, char *grad_scratch, int clear,
+                                  void *stream, int debug)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail("surfel_classes_backward_blend", "bad sizes");
+    if (n_classes < 1 || n_classes > MAX_CLASSES) return fail("surfel_classes_backward_blend", "between 1 and 8 classes per pass");
+    if (P == 0) return 0;
+    if (!background || !geometry_buffer || !image_buffer || !dL_dprobs || !grad_scratch)
+        return fail("surfel_classes_backward_blend", "NULL required pointer");
+    if (num_rendered > 0 && !binning_buffer) return fail("surfel_classes_backward_blend", "NULL binning_buffer");
+    GeomView g = carve_geom(geometry_buffer, P, depth_sort_temp_bytes(P));
+    ImageView iv = carve_image(image_buffer, width, height);
+    BinView bv{};
+    if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
+    return backward_blend(P, width, height, num_rendered, background, g, iv, bv, dL_dprobs, nullptr, grad_scratch,
+                          clear != 0, st, debug, n_classes);
 }
 
 int surfel_mark_visible(int P, const float *means3D, const float *viewmatrix, const float *projmatrix,

@@ -44,6 +44,9 @@ constexpr int REC_BYTES = REC_FLOATS * 4;
 //   [15..17] dL_dnormal, [18..19] pad
 constexpr int GACC_FLOATS = 20;
 
+// Class-probability pass (render_fwd.cu / render_bwd.cu, CLASSES = true): channels rendered in one traversal.
+constexpr int MAX_CLASSES = 8;
+
 template <typename T>
 __host__ __device__ inline T *carve(char *&p, size_t count)
 {

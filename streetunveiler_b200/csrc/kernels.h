@@ -23,6 +23,7 @@ void launch_preprocess_fwd(const PreprocessFwdArgs &a, cudaStream_t stream);
 // colour passes over one geometry state: rewrite the rgb words of the packed records / move the colour gradient out
 void launch_set_record_colors(int P, const float *colors, float *rec, cudaStream_t stream);
 void launch_take_color_grad(int P, float *gacc, float *dL_dcolor, cudaStream_t stream);
+void launch_set_record_labels(int P, const int *labels, float *rec, cudaStream_t stream);
 void launch_mark_visible(int P, const float *means3D, const float *viewmatrix, unsigned char *present,
                          cudaStream_t stream);
 
@@ -83,6 +84,7 @@ struct RenderFwdArgs {
     uint32_t *tile_max_contrib;
     float *out_color, *out_others;
     int subtile_cull;
+    int n_classes = 0;  // > 0: class-probability pass (out_color = [n_classes,H,W], bg = [n_classes], out_others unused)
 };
 void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream);
 
@@ -102,6 +104,7 @@ struct RenderBwdArgs {
     int subtile_cull;
     int *aux_flag = nullptr;  // one scratch word for the "any depth/normal/distortion gradient?" flag, or nullptr
     int variant = 0;          // kernel selection, see launch_render_bwd ("bwd_variant" option)
+    int n_classes = 0;        // > 0: backward of the class-probability pass (dL_dpix = [n_classes,H,W], bg = [n_classes])
 };
 void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream);
 

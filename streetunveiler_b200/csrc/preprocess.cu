@@ -411,6 +411,20 @@ __global__ void take_color_grad_kernel(const int P, float *__restrict__ gacc, fl
     }
 }
 
+// class-probability pass: word 15 carries the class label (int bits; negative = contributes to no class)
+__global__ void set_record_labels_kernel(const int P, const int *__restrict__ labels, float *__restrict__ rec)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    rec[(size_t)idx * REC_FLOATS + 15] = __int_as_float(labels[idx]);
+}
+
+void launch_set_record_labels(int P, const int *labels, float *rec, cudaStream_t stream)
+{
+    if (P == 0) return;
+    set_record_labels_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, labels, rec);
+}
+
 void launch_set_record_colors(int P, const float *colors, float *rec, cudaStream_t stream)
 {
     if (P == 0) return;

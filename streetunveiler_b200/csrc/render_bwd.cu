@@ -83,9 +83,13 @@ __global__ void __launch_bounds__(256) aux_zero_scan_kernel(const float *__restr
 // CULL: sub-tile culling on.  AUX: see above.  REGS: register cap -- 72 registers put three 9-warp CTAs on an SM instead
 // of two (the kernel is issue-bound with few resident warps: measured -20 % for AUX = false despite ~70 B of spills).
 // (Tried and dropped: direct per-lane reductions when only 1-2 pixels of a warp contribute -- slower than the butterfly.)
-template <bool CULL, bool AUX, int REGS>
+// CLASSES: backward of the class-probability pass (render_fwd.cu).  With one-hot "colours" the three colour recurrences
+// collapse into ONE scalar: sum_k (c_k - accum_rec_k) dL/dpixel_k = dL/dpixel_label - S with
+// S <- alpha dL/dpixel_label + (1 - alpha) S, for any number of channels; labels are not trainable, so the colour
+// gradient words are not produced (12 values per instance through the butterfly instead of 15).  Requires AUX = false.
+template <bool CULL, bool AUX, int REGS, bool CLASSES>
 __global__ void __maxnreg__(REGS)
-render_bwd_kernel(const int *__restrict__ aux_flag,
+render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                   const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
                   const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
@@ -132,11 +136,15 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
     const int median_contributor = inside ? (int)n_contrib[pix_id + HW] : 0;
     const uint32_t median_match = (uint32_t)(median_contributor - 1);  // backward.cu:347, unsigned compare
 
-    float accum_rec[3] = {0.f, 0.f, 0.f}, dL_dpixel[3] = {0.f, 0.f, 0.f};
+    static_assert(!(CLASSES && AUX), "the class-probability pass has no depth/normal/distortion outputs");
+    constexpr int NC = CLASSES ? MAX_CLASSES : 3;
+    float accum_rec[3] = {0.f, 0.f, 0.f}, dL_dpixel[NC];   // CLASSES: accum_rec[0] is the scalar S
+#pragma unroll
+    for (int k = 0; k < NC; k++) dL_dpixel[k] = 0.f;
     float dL_dreg = 0.f, dL_ddepth = 0.f, dL_daccum = 0.f, dL_dmedian_depth = 0.f;
     float dL_dnormal2D[3] = {0.f, 0.f, 0.f};
     if (inside) {
-        dL_daccum = dL_dothers[HW + pix_id];
+        if (!CLASSES) dL_daccum = dL_dothers[HW + pix_id];
         if (AUX) {
             dL_ddepth = dL_dothers[pix_id];
             dL_dnormal2D[0] = dL_dothers[2 * HW + pix_id];
@@ -145,9 +153,9 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
             dL_dmedian_depth = dL_dothers[5 * HW + pix_id];
             dL_dreg = dL_dothers[6 * HW + pix_id];
         }
-        dL_dpixel[0] = dL_dpixels[pix_id];
-        dL_dpixel[1] = dL_dpixels[HW + pix_id];
-        dL_dpixel[2] = dL_dpixels[2 * HW + pix_id];
+#pragma unroll
+        for (int k = 0; k < NC; k++)
+            if (!CLASSES || k < n_classes) dL_dpixel[k] = dL_dpixels[k * HW + pix_id];
     }
     float accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
     float accum_normal_rec[3] = {0.f, 0.f, 0.f};
@@ -156,7 +164,8 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
     const float final_A = 1 - T_final;
     float bg_dot_dpixel = 0;
 #pragma unroll
-    for (int i = 0; i < 3; i++) bg_dot_dpixel += bg[i] * dL_dpixel[i];
+    for (int i = 0; i < NC; i++)
+        if (!CLASSES || i < n_classes) bg_dot_dpixel += bg[i] * dL_dpixel[i];
 
     // highest list position any pixel of this warp blended, +1
     uint32_t warp_last = last_contributor;
@@ -165,6 +174,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
 
     const int my_slot = Butterfly<NV, 4>::slot(lane, 0, NV);
     const int my_slot15 = Butterfly<15, 4>::slot(lane, 0, 15);  // without the three normal gradients
+    const int my_slot12 = Butterfly<12, 4>::slot(lane, 0, 12);  // CLASSES: without the colour gradients either
 
     // ... and within a frame that has some, skip their recurrences for warps none of whose pixels has any.
     const bool aux_any = AUX && __any_sync(0xffffffffu, dL_ddepth != 0.f || dL_dreg != 0.f || dL_dmedian_depth != 0.f ||
@@ -232,9 +242,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
                             if (!(alpha < ALPHA_MIN)) {
                                 valid = true;
                                 const float4 q3 = r4[3];
-                                const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
                                 const float normal[3] = {q3.x, q3.y, q3.z};
-                                const float col[3] = {q3.w, q4.x, q4.y};
 
                                 // The reference keeps (last_alpha, last_color, ...) and folds them into the
                                 // suffix accumulators at the NEXT contributor (backward.cu:329,365-374); folding
@@ -246,12 +254,23 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
                                 T = T / one_m_alpha;
                                 const float w = alpha * T;
                                 float dL_dalpha = 0.0f;
+                                if constexpr (CLASSES) {
+                                    const int label = __float_as_int(q3.w);   // warp-uniform
+                                    float g_label = 0.f;
 #pragma unroll
-                                for (int ch = 0; ch < 3; ch++) {
-                                    const float cc = col[ch];
-                                    dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
-                                    accum_rec[ch] = alpha * cc + one_m_alpha * accum_rec[ch];
-                                    v[12 + ch] = w * dL_dpixel[ch];
+                                    for (int k = 0; k < NC; k++) g_label = (label == k) ? dL_dpixel[k] : g_label;
+                                    dL_dalpha = g_label - accum_rec[0];
+                                    accum_rec[0] = alpha * g_label + one_m_alpha * accum_rec[0];
+                                } else {
+                                    const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
+                                    const float col[3] = {q3.w, q4.x, q4.y};
+#pragma unroll
+                                    for (int ch = 0; ch < 3; ch++) {
+                                        const float cc = col[ch];
+                                        dL_dalpha += (cc - accum_rec[ch]) * dL_dpixel[ch];
+                                        accum_rec[ch] = alpha * cc + one_m_alpha * accum_rec[ch];
+                                        v[12 + ch] = w * dL_dpixel[ch];
+                                    }
                                 }
                                 float dL_dz = 0.0f;
                                 if (aux_any) {  // warp-uniform: some pixel of this warp has depth/normal/distortion gradients
@@ -274,8 +293,10 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
                                     }
                                     dL_dz += w * dL_ddepth;
                                 }
-                                dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
-                                accum_alpha_rec = alpha + one_m_alpha * accum_alpha_rec;
+                                if (!CLASSES) {   // the class pass has no alpha-channel output
+                                    dL_dalpha += (1 - accum_alpha_rec) * dL_daccum;
+                                    accum_alpha_rec = alpha + one_m_alpha * accum_alpha_rec;
+                                }
                                 dL_dalpha *= T;
                                 dL_dalpha += (-T_final * fast_rcp(one_m_alpha)) * bg_dot_dpixel;
 
@@ -311,7 +332,10 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
                 }
                 if (__any_sync(0xffffffffu, valid)) {
                     float *dst = gacc + (size_t)ring.id[stage][jj] * GACC_FLOATS;
-                    if (aux_any) {
+                    if constexpr (CLASSES) {
+                        Butterfly<12, 4>::run(v, lane);
+                        if (my_slot12 >= 0) red_add_f32(dst + my_slot12, v[0]);
+                    } else if (aux_any) {
                         Butterfly<NV, 4>::run(v, lane);
                         if (my_slot >= 0) red_add_f32(dst + my_slot, v[0]);
                     } else {  // v[15..17] (normal gradients) are identically zero: 16 shuffles instead of 20
@@ -327,12 +351,12 @@ render_bwd_kernel(const int *__restrict__ aux_flag,
     }
 }
 
-template <bool CULL, bool AUX, int REGS>
+template <bool CULL, bool AUX, int REGS, bool CLASSES = false>
 static void launch_one(const RenderBwdArgs &a, const int tiles, const int *flag, cudaStream_t stream)
 {
-    auto k = render_bwd_kernel<CULL, AUX, REGS>;
+    auto k = render_bwd_kernel<CULL, AUX, REGS, CLASSES>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<BWD_STAGES>));  // per device, cheap
-    k<<<tiles, TILE_THREADS, sizeof(TileRing<BWD_STAGES>), stream>>>(flag, a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list,
+    k<<<tiles, TILE_THREADS, sizeof(TileRing<BWD_STAGES>), stream>>>(flag, a.n_classes, a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list,
                                                                       a.rec, a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
                                                                       a.dL_dpix, a.dL_dothers, a.gacc);
 }
@@ -342,6 +366,10 @@ void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
     const int rows = a.gy > a.row_offset ? (a.gy - a.row_offset + a.row_stride - 1) / a.row_stride : 0;
     const int tiles = a.gx * rows;
     if (tiles == 0) return;
+    if (a.n_classes > 0) {   // class-probability pass: no aux outputs exist
+        launch_one<true, false, 72, true>(a, tiles, nullptr, stream);
+        return;
+    }
     if (!a.subtile_cull) {   // debugging aid only
         launch_one<false, true, 96>(a, tiles, nullptr, stream);
         return;
@@ -352,11 +380,13 @@ void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
     }
     cudaMemsetAsync(a.aux_flag, 0, sizeof(int), stream);
     aux_zero_scan_kernel<<<148 * 4, 256, 0, stream>>>(a.dL_dothers, (size_t)a.W * a.H, a.aux_flag);
-    switch (a.variant) {   // 1 is the default (api.cu); the others are kept for the occupancy experiment in tools/bench_variants.py
-    case 2:  launch_one<true, false, 72>(a, tiles, a.aux_flag, stream); launch_one<true, true, 72>(a, tiles, a.aux_flag, stream); break;
+    // 2 is the default (api.cu).  Measured at 2M surfels (tools/bench_variants.py, ms for colour+alpha | all gradients):
+    // v0 3.14 | 3.49, v1 2.64 | 3.51, v2 2.63 | 3.42, v3 2.98 | 3.51, v4 3.12 | 3.85.
+    switch (a.variant) {
+    case 1:  launch_one<true, false, 72>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96>(a, tiles, a.aux_flag, stream); break;
     case 3:  launch_one<true, false, 56>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96>(a, tiles, a.aux_flag, stream); break;
     case 4:  launch_one<true, false, 96>(a, tiles, a.aux_flag, stream); launch_one<true, true, 80>(a, tiles, a.aux_flag, stream); break;
-    default: launch_one<true, false, 72>(a, tiles, a.aux_flag, stream); launch_one<true, true, 96>(a, tiles, a.aux_flag, stream); break;
+    default: launch_one<true, false, 72>(a, tiles, a.aux_flag, stream); launch_one<true, true, 72>(a, tiles, a.aux_flag, stream); break;
     }
 }
 

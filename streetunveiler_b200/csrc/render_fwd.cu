@@ -22,9 +22,15 @@
 
 namespace surfel {
 
-template <bool CULL>
+// CLASSES = false: the operator's colour pass (3 colour channels + the 7 allmap channels).
+// CLASSES = true:  class-probability pass: word 15 of the record holds a class label instead of
+//   red, the pass accumulates w into the label's channel -- bit for bit what the reference gets from one-hot
+//   "colours" (1 * w and 0 * w are exact) -- for up to MAX_CLASSES channels in ONE traversal of the lists, and writes
+//   only the class images plus the per-pixel state the backward needs (T, last contributor).
+template <bool CULL, bool CLASSES>
 __global__ void __launch_bounds__(TILE_THREADS)
-render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
+render_fwd_kernel(const int n_classes,
+                  const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
                   const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
                   const float *__restrict__ bg, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
@@ -63,7 +69,10 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
 
     bool done = !inside;
     float T = 1.0f;
-    float C[3] = {0.f, 0.f, 0.f}, N[3] = {0.f, 0.f, 0.f};
+    constexpr int NC = CLASSES ? MAX_CLASSES : 3;
+    float C[NC], N[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NC; k++) C[k] = 0.f;
     float Dacc = 0.f, M1 = 0.f, M2 = 0.f, distortion = 0.f, median_depth = 0.f;
     uint32_t last_contributor = 0, median_contributor = 0;  // float -1 -> u32 saturates to 0 (quirk 8)
 
@@ -116,25 +125,31 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
                                         done = true;
                                     } else {
                                         const float4 q3 = r4[3];
-                                        const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
                                         const uint32_t contributor = (uint32_t)(c * CHUNK + jj + 1);
                                         const float w = alpha * T;
-                                        const float A = 1 - T;
-                                        const float m = FAR_N / (FAR_N - NEAR_N) * (1 - NEAR_N / depth);
-                                        distortion += (m * m * A + M2 - 2 * m * M1) * w;
-                                        Dacc += depth * w;
-                                        M1 += m * w;
-                                        M2 += m * m * w;
-                                        if (T > 0.5f) {
-                                            median_depth = depth;
-                                            median_contributor = contributor;
+                                        if constexpr (CLASSES) {
+                                            const int label = __float_as_int(q3.w);   // warp-uniform
+#pragma unroll
+                                            for (int k = 0; k < NC; k++) C[k] += (label == k) ? w : 0.f;
+                                        } else {
+                                            const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
+                                            const float A = 1 - T;
+                                            const float m = FAR_N / (FAR_N - NEAR_N) * (1 - NEAR_N / depth);
+                                            distortion += (m * m * A + M2 - 2 * m * M1) * w;
+                                            Dacc += depth * w;
+                                            M1 += m * w;
+                                            M2 += m * m * w;
+                                            if (T > 0.5f) {
+                                                median_depth = depth;
+                                                median_contributor = contributor;
+                                            }
+                                            N[0] += q3.x * w;
+                                            N[1] += q3.y * w;
+                                            N[2] += q3.z * w;
+                                            C[0] += q3.w * w;
+                                            C[1] += q4.x * w;
+                                            C[2] += q4.y * w;
                                         }
-                                        N[0] += q3.x * w;
-                                        N[1] += q3.y * w;
-                                        N[2] += q3.z * w;
-                                        C[0] += q3.w * w;
-                                        C[1] += q4.x * w;
-                                        C[2] += q4.y * w;
                                         T = test_T;
                                         last_contributor = contributor;
                                     }
@@ -169,9 +184,15 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
         const size_t HW = (size_t)W * H;
         const size_t pix_id = (size_t)W * pix_y + pix_x;
         final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+        if constexpr (CLASSES) {
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                if (k < n_classes) out_color[pix_id + k * HW] = C[k] + T * bg[k];
+            return;
+        }
         final_T[pix_id + HW] = M1;
         final_T[pix_id + 2 * HW] = M2;
-        n_contrib[pix_id] = last_contributor;
         n_contrib[pix_id + HW] = median_contributor;
         out_color[pix_id] = C[0] + T * bg[0];
         out_color[pix_id + HW] = C[1] + T * bg[1];
@@ -186,23 +207,27 @@ render_fwd_kernel(const int W, const int H, const int gx, const uint32_t *__rest
     }
 }
 
+template <bool CULL, bool CLASSES>
+static void launch_fwd(const RenderFwdArgs &a, const int tiles, cudaStream_t stream)
+{
+    auto k = render_fwd_kernel<CULL, CLASSES>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<FWD_STAGES>));  // per device, cheap
+    k<<<tiles, TILE_THREADS, sizeof(TileRing<FWD_STAGES>), stream>>>(a.n_classes, a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list,
+                                                                      a.rec, a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
+                                                                      a.out_color, a.out_others);
+}
+
 void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream)
 {
     const int rows = a.gy > a.row_offset ? (a.gy - a.row_offset + a.row_stride - 1) / a.row_stride : 0;
     const int tiles = a.gx * rows;
     if (tiles == 0) return;
-    {  // per device and cheap: opt in to more than 48 KB of dynamic shared memory
-        cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<FWD_STAGES>));
-        cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<FWD_STAGES>));
-    }
-    if (a.subtile_cull)
-        render_fwd_kernel<true><<<tiles, TILE_THREADS, sizeof(TileRing<FWD_STAGES>), stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec,
-                                                                    a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
-                                                                    a.out_color, a.out_others);
+    if (a.n_classes > 0)
+        launch_fwd<true, true>(a, tiles, stream);
+    else if (a.subtile_cull)
+        launch_fwd<true, false>(a, tiles, stream);
     else
-        render_fwd_kernel<false><<<tiles, TILE_THREADS, sizeof(TileRing<FWD_STAGES>), stream>>>(a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list, a.rec,
-                                                                     a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
-                                                                     a.out_color, a.out_others);
+        launch_fwd<false, false>(a, tiles, stream);
 }
 
 }  // namespace surfel

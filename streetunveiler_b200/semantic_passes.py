@@ -1,11 +1,13 @@
-"""render_semantic on shared binning ("next" row 2).
+"""render_semantic in one rasterizer traversal ("next" row 2).
 
 ``render_semantic`` has the signature and return dict of the reference's ``gaussian_renderer.render_semantic``
 (gaussian_renderer/__init__.py:327-460): per-class probability images rendered from one-hot "colours", three classes
 per rasterizer pass, the background one-hot at the sky class.  The reference issues ceil(6/3) = 2 complete rasterizer
-calls (each with its own projection, sorts, binning and backward); here both passes share one geometry / binning state
-(``rasterize_color_passes``).  The reference's own file keeps running unchanged on the drop-in rasterizer -- this module
-is the optional faster caller, like ``surface_epilogue.render``.
+calls (each with its own projection, sorts, binning and backward); here all classes come out of ONE blend pass over the
+per-Gaussian labels (``rasterize_class_probabilities``; up to 8 classes), or -- ``single_pass=False``, any number of
+classes -- from colour passes that share one geometry / binning state (``rasterize_color_passes``).  The reference's own
+file keeps running unchanged on the drop-in rasterizer -- this module is the optional faster caller, like
+``surface_epilogue.render``.
 """
 from __future__ import annotations
 
@@ -16,6 +18,7 @@ import numpy as np
 import torch
 
 from .diff_surfel_rasterization import GaussianRasterizationSettings
+from .diff_surfel_rasterization.class_pass import MAX_CLASSES, rasterize_class_probabilities
 from .diff_surfel_rasterization.color_passes import rasterize_color_passes
 
 # utils/semantic_utils.py:100-102 (the six classes StreetUnveiler trains on) and :14-21 (their display colours)
@@ -33,7 +36,7 @@ def one_hot_colors(semantics_tag: torch.Tensor, first_class: int, num_classes: i
 
 def render_semantic(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0,
                     semantic_filter_bit: Optional[int] = None, reverse_semantic: Optional[bool] = None,
-                    classes: Sequence[str] = CONCERNED_CLASSES):
+                    classes: Sequence[str] = CONCERNED_CLASSES, single_pass: bool = True):
     n_cls = len(classes)
     sky = list(classes).index("sky")
     dev = pc.get_xyz.device
@@ -72,10 +75,17 @@ def render_semantic(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_
         scales, rotations = sel(pc.get_scaling), sel(pc.get_rotation)
     semantics_tag = sel(pc.get_semantics)
 
-    colors = [one_hot_colors(semantics_tag, i, n_cls) for i in range(0, n_cls, 3)]
-    images, _radii, _allmap = rasterize_color_passes(settings, means3D, means2D, opacity, colors, bgs, scales=scales,
-                                                     rotations=rotations, cov3D_precomp=cov3D_precomp)
-    output_semantic = torch.cat([img[:min(3, n_cls - 3 * k)] for k, img in enumerate(images)], dim=0)
+    if single_pass and n_cls <= MAX_CLASSES:
+        labels = semantics_tag.reshape(-1).to(torch.int32)
+        bg_vec = torch.tensor(bg_prob, dtype=torch.float32, device=dev)
+        output_semantic, _radii = rasterize_class_probabilities(settings, means3D, means2D, opacity, labels, bg_vec,
+                                                                scales=scales, rotations=rotations,
+                                                                cov3D_precomp=cov3D_precomp)
+    else:
+        colors = [one_hot_colors(semantics_tag, i, n_cls) for i in range(0, n_cls, 3)]
+        images, _radii, _allmap = rasterize_color_passes(settings, means3D, means2D, opacity, colors, bgs, scales=scales,
+                                                         rotations=rotations, cov3D_precomp=cov3D_precomp)
+        output_semantic = torch.cat([img[:min(3, n_cls - 3 * k)] for k, img in enumerate(images)], dim=0)
 
     topk_values, _ = torch.topk(output_semantic, k=2, dim=0)
     uncertainty = 1.0 - (topk_values[0, ...] - topk_values[1, ...])

@@ -156,8 +156,9 @@ def reference_formulation_semantic(view, pc, filter_bit, reverse):
     return torch.cat(out, 0)
 
 
+@pytest.mark.parametrize("single_pass", [True, False])
 @pytest.mark.parametrize("filter_bit,reverse", [(None, None), (1 << 2, True), (1 << 4, False)])
-def test_render_semantic_matches_reference_formulation(filter_bit, reverse):
+def test_render_semantic_matches_reference_formulation(filter_bit, reverse, single_pass):
     from streetunveiler_b200.semantic_passes import render_semantic
     from test_epilogue_gpu import view_of
     dev = torch.device("cuda")
@@ -171,7 +172,8 @@ def test_render_semantic_matches_reference_formulation(filter_bit, reverse):
         return torch.nn.functional.cross_entropy(sem.unsqueeze(0), gt.unsqueeze(0), weight=w)
 
     pc, p = fake_model(15_000, dev, 51)
-    pkg = render_semantic(view, pc, pipe, torch.zeros(3, device=dev), semantic_filter_bit=filter_bit, reverse_semantic=reverse)
+    pkg = render_semantic(view, pc, pipe, torch.zeros(3, device=dev), semantic_filter_bit=filter_bit, reverse_semantic=reverse,
+                          single_pass=single_pass)
     assert pkg["render_semantics"].shape == (6, cam.height, cam.width)
     assert pkg["semantic_rgb"].shape == (3, cam.height, cam.width) and pkg["semantic_uncertainty"].shape == (cam.height, cam.width)
     loss_of(pkg["render_semantics"]).backward()
@@ -181,3 +183,71 @@ def test_render_semantic_matches_reference_formulation(filter_bit, reverse):
     assert torch.equal(pkg["render_semantics"].detach(), sem2.detach())
     for k in p:
         assert hz.rel_err(p[k].grad.cpu().numpy(), p2[k].grad.cpu().numpy()) <= 2e-5, k
+
+
+@pytest.mark.parametrize("n_classes", [1, 6, 8])
+def test_class_probability_pass_equals_one_hot_colour_passes(n_classes):
+    """One traversal with labels == one rasterizer call per three one-hot colours (images bit-identical), including a
+    label outside the class range (contributes to nothing) and an arbitrary background vector."""
+    from streetunveiler_b200.diff_surfel_rasterization.class_pass import rasterize_class_probabilities
+    from streetunveiler_b200.semantic_passes import one_hot_colors
+    dev = torch.device("cuda")
+    mod = hz.ours_module()
+    cam = syn.cam_tilted(320, 208, 260.0)
+    P = 20_000
+    sc = syn.box_scene(P, 61, 0)
+    g = torch.Generator().manual_seed(n_classes)
+    labels = torch.randint(-1, n_classes + 1, (P,), generator=g, dtype=torch.int32).to(dev)
+    bg = torch.rand(n_classes, generator=g).to(dev)
+    up = (torch.randn(n_classes, cam.height, cam.width, generator=g) / (cam.height * cam.width)).to(dev)
+
+    p = leaves_of(sc, dev)
+    probs, radii = rasterize_class_probabilities(hz._settings(mod, cam, torch.zeros(3), 0, 1.0, dev), p["means3D"], p["means2D"],
+                                                 p["opacities"], labels, bg, scales=p["scales"], rotations=p["rotations"])
+    probs.backward(up)
+
+    q = leaves_of(sc, dev)
+    imgs = []
+    for i in range(0, n_classes, 3):
+        k = min(3, n_classes - i)
+        bg3 = torch.cat([bg[i:i + k], torch.zeros(3 - k, device=dev)])
+        rast = mod.GaussianRasterizer(hz._settings(mod, cam, bg3.cpu(), 0, 1.0, dev))
+        img, r2, _ = rast(means3D=q["means3D"], means2D=q["means2D"], opacities=q["opacities"],
+                          colors_precomp=one_hot_colors(labels.reshape(-1, 1), i, n_classes), scales=q["scales"], rotations=q["rotations"])
+        imgs.append(img[:k])
+    ref = torch.cat(imgs, 0)
+    ref.backward(up)
+    assert torch.equal(radii, r2) and torch.equal(probs.detach(), ref.detach())
+    for k in p:
+        assert hz.rel_err(p[k].grad.cpu().numpy(), q[k].grad.cpu().numpy()) <= 2e-5, (k, hz.rel_err(p[k].grad.cpu().numpy(), q[k].grad.cpu().numpy()))
+
+
+@pytest.mark.skipif(not hz.reference_available(), reason="oracle/_ref (reference extension) not built")
+def test_class_probability_pass_against_reference_extension():
+    from streetunveiler_b200.diff_surfel_rasterization.class_pass import rasterize_class_probabilities
+    from streetunveiler_b200.semantic_passes import one_hot_colors
+    dev = torch.device("cuda")
+    cam = syn.cam_a()
+    P = 200_000
+    sc = syn.street_scene(P, 5, 0)
+    g = torch.Generator().manual_seed(3)
+    labels = torch.randint(0, 6, (P,), generator=g, dtype=torch.int32).to(dev)
+    bg = torch.tensor([0., 0., 0., 0., 1., 0.], device=dev)
+    up = (torch.randn(6, cam.height, cam.width, generator=g) / (cam.height * cam.width)).to(dev)
+    p = leaves_of(sc, dev)
+    probs, _ = rasterize_class_probabilities(hz._settings(hz.ours_module(), cam, torch.zeros(3), 0, 1.0, dev), p["means3D"],
+                                             p["means2D"], p["opacities"], labels, bg, scales=p["scales"], rotations=p["rotations"])
+    probs.backward(up)
+    ref_mod = hz.reference_module()
+    q = leaves_of(sc, dev)
+    imgs = []
+    for i in (0, 3):
+        rast = ref_mod.GaussianRasterizer(hz._settings(ref_mod, cam, bg[i:i + 3].cpu(), 0, 1.0, dev))
+        img, _, _ = rast(means3D=q["means3D"], means2D=q["means2D"], opacities=q["opacities"],
+                         colors_precomp=one_hot_colors(labels.reshape(-1, 1), i, 6), scales=q["scales"], rotations=q["rotations"])
+        imgs.append(img)
+    ref = torch.cat(imgs, 0)
+    ref.backward(up)
+    assert hz.rel_err(probs.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= 1e-6
+    for k in p:
+        assert hz.rel_err(p[k].grad.cpu().numpy(), q[k].grad.cpu().numpy()) <= 1e-4, (k, hz.rel_err(p[k].grad.cpu().numpy(), q[k].grad.cpu().numpy()))

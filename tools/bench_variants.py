@@ -1,5 +1,5 @@
 """Backward-blend kernel variants (surfel_set_option "bwd_variant": 0 = one kernel, 96 registers; 1 = device-side choice
-between the colour+alpha-only kernel at 72 registers and the full one at 96 (default); 2 = both at 72; 3 = 56 | 96;
+between the colour+alpha-only kernel at 72 registers and the full one at 96; 2 = both at 72 (default); 3 = 56 | 96;
 4 = 92 | 80) at benchmark size: stage time of render_bwd for
 colour+alpha gradients (BASELINE configs 2/3/5) and for all ten gradient planes (config 4).  GPU box."""
 import json, os, sys

@@ -10,12 +10,12 @@ run() { name=$1; shift; timeout 300 "$@" > gpurun_out/$name.json 2> gpurun_out/$
 run bench_variants python tools/bench_variants.py
 BENCH_E2E_TRACE=1 run bench python bench.py
 run bench_ref python bench.py --impl reference
-run bench_adam python tools/bench_adam.py
-ADAM_DENSE=1 run bench_adam_dense python tools/bench_adam.py
+run bench_semantic python tools/bench_semantic.py
 if [ "$1" = "full" ]; then
   run bench_loss python tools/bench_loss.py
   run bench_epilogue python tools/bench_epilogue.py
-  run bench_semantic python tools/bench_semantic.py
+  run bench_adam python tools/bench_adam.py
+  ADAM_DENSE=1 run bench_adam_dense python tools/bench_adam.py
   run bench_iteration python tools/bench_iteration.py
   run pcie python tools/pcie_probe.py
 fi
