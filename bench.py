@@ -41,9 +41,10 @@ from streetunveiler_b200 import synthetic as syn  # noqa: E402
 METRIC = "M Gaussians/s fwd+bwd @1920x1280"
 UNIT = "MGaussians/s"
 P_PER_GPU = 2_000_000
-# preprocess_fwd, 6 radix passes x (histogram, row scan, scatter), 3 scan kernels, emit_instances, tile_ranges,
-# order_tiles, render_fwd, render_bwd, preprocess_bwd -- every one hand-written (no library kernels on the path)
-HAND_WRITTEN_LAUNCHES_PER_STEP = 1 + 6 * 3 + 3 + 1 + 1 + 1 + 1 + 1 + 1
+# preprocess_fwd, 6 radix passes x (histogram, row scan, scatter), 3 scan kernels, publish_u32 (num_rendered read-back),
+# emit_instances, tile_ranges, order_tiles, render_fwd, aux_zero_scan, render_bwd x 2 specialisations (one returns at
+# once), preprocess_bwd -- every one hand-written (no library kernels on the path)
+HAND_WRITTEN_LAUNCHES_PER_STEP = 1 + 6 * 3 + 3 + 1 + 1 + 1 + 1 + 1 + 1 + 2 + 1
 
 
 # ------------------------------------------------------------------------------------------------
@@ -429,9 +430,11 @@ def run_ours(args):
         "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": HAND_WRITTEN_LAUNCHES_PER_STEP * args.steps,
-        "gpu_launches_note": "per step: preprocess_fwd, 6 radix-sort passes x 3 kernels, 3 scan kernels, emit_instances, "
-                             "tile_ranges, order_tiles, render_fwd, render_bwd, preprocess_bwd (+1 count_window_tiles per "
-                             "rank when sharded; 2 memsets not counted); all hand-written, see profiles/r01_launches_final.md",
+        "gpu_launches_note": "per step: preprocess_fwd, 6 radix-sort passes x 3 kernels, 3 scan kernels, publish_u32, "
+                             "emit_instances, tile_ranges, order_tiles, render_fwd, aux_zero_scan, 2 render_bwd "
+                             "specialisations (one returns at once), preprocess_bwd (sharded: +1 count_window_tiles, one "
+                             "render_bwd, no aux_zero_scan; memsets not counted); all hand-written, see "
+                             "profiles/r01_launches_final.md",
         "roofline": roof,
         "step_roofline": {"alg_bytes": int(step_bytes), "achieved_gbs": round(step_bytes / (ms_step * 1e-3) / 1e9, 2),
                           "frac_of_peak": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),
