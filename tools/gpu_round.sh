@@ -19,4 +19,10 @@ if [ "$1" = "full" ]; then
   run bench_iteration python tools/bench_iteration.py
   run pcie python tools/pcie_probe.py
 fi
+if [ "$1" = "full" ] || [ "$1" = "profile" ]; then
+  # ncu passes (never a source of bench numbers): launch list of the benchmark step, full captures of the blend kernels
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:render_ -s 6 -c 3 -o gpurun_out/r01f_render -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_render.log 2>&1; echo "ncu render rc=$?"
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:render_ -c 2 -o gpurun_out/r01f_classes -f python tools/bench_semantic.py > gpurun_out/ncu_classes.log 2>&1; echo "ncu classes rc=$?"
+fi
 ls -la gpurun_out
