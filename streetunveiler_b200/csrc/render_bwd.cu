@@ -74,9 +74,26 @@ __global__ void __launch_bounds__(256) aux_zero_scan_kernel(const float *__restr
                                                             int *__restrict__ flag)
 {
     bool any = false;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (size_t)gridDim.x * blockDim.x)
-        any |= dL_dothers[p] != 0.f || dL_dothers[2 * HW + p] != 0.f || dL_dothers[3 * HW + p] != 0.f ||
-               dL_dothers[4 * HW + p] != 0.f || dL_dothers[5 * HW + p] != 0.f || dL_dothers[6 * HW + p] != 0.f;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dothers) & 15) == 0) {
+        // channel 0 and channels 2..6 as 128-bit words, four independent loads in flight per thread
+        const float4 *v = reinterpret_cast<const float4 *>(dL_dothers);
+        const size_t q = HW / 4, n = 6 * q;
+        for (size_t i0 = tid; i0 < n; i0 += 4 * nthreads) {
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const size_t i = i0 + u * nthreads;
+                x[u] = i < n ? v[i < q ? i : i + q] : make_float4(0.f, 0.f, 0.f, 0.f);   // skip channel 1 (alpha)
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) any |= x[u].x != 0.f || x[u].y != 0.f || x[u].z != 0.f || x[u].w != 0.f;
+        }
+    } else {
+        for (size_t p = tid; p < HW; p += nthreads)
+            any |= dL_dothers[p] != 0.f || dL_dothers[2 * HW + p] != 0.f || dL_dothers[3 * HW + p] != 0.f ||
+                   dL_dothers[4 * HW + p] != 0.f || dL_dothers[5 * HW + p] != 0.f || dL_dothers[6 * HW + p] != 0.f;
+    }
     if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;   // benign race: every writer stores 1
 }
 
