@@ -114,6 +114,7 @@ ImageView carve_image(char *base, int W, int H)
     v.n_contrib = carve<uint32_t>(p, 2 * HW);
     v.tile_max_contrib = carve<uint32_t>(p, tiles);
     v.tile_order = carve<uint32_t>(p, tiles);
+    v.aux_flag = carve<int>(p, 1);
     return v;
 }
 
@@ -333,8 +334,7 @@ size_t surfel_image_bytes(int width, int height)
 {
     if (width <= 0 || height <= 0) { fail("surfel_image_bytes", "bad image size"); return 0; }
     ImageView v = carve_image(nullptr, width, height);
-    const size_t tiles = (size_t)((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
-    return (size_t)(v.tile_order + tiles) + 128;
+    return (size_t)(v.aux_flag + 1) + 128;
 }
 
 size_t surfel_binning_bytes(int64_t num_rendered)
@@ -804,6 +804,7 @@ int surfel_window_backward(int P_total, int width, int height, int row_offset, i
     r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = records; r.bg = background;
     r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
     r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = grad_records; r.subtile_cull = g_subtile_cull;
+    r.aux_flag = iv.aux_flag; r.variant = g_bwd_variant;
     launch_render_bwd(r, st);
     STAGE("render backward");
     return 0;

@@ -76,6 +76,7 @@ struct ImageView {
     uint32_t *n_contrib; // [2][HW]  last contributor, median contributor
     uint32_t *tile_max_contrib; // [tiles] max over the tile's pixels of last contributor
     uint32_t *tile_order;       // [tiles] launch order (longest lists first)
+    int *aux_flag;              // one word: "some depth/normal/distortion gradient is non-zero" (render_bwd.cu)
 };
 
 struct BinView {

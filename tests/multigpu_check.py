@@ -1,7 +1,10 @@
 """Run under torchrun (one rank per GPU): sharded rasterization must equal the single-GPU operator.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/multigpu_check.py [P]
+        tests/multigpu_check.py [P] [all|color_alpha]
+
+The second argument picks the upstream gradients: "all" exercises the full backward-blend specialisation, "color_alpha"
+the colour+alpha one that the device-side flag selects when the depth/normal/distortion gradients are zero.
 """
 import os
 import sys
@@ -26,7 +29,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     cam = syn.make_camera(960, 640, 1027.5, 1027.5)
     scene = syn.street_scene(P, 4, 3)
-    grads = syn.upstream_grads(cam.width, cam.height, "all", seed=11)
+    mode = sys.argv[2] if len(sys.argv) > 2 else "all"
+    grads = syn.upstream_grads(cam.width, cam.height, mode, seed=11)
     bg = torch.tensor([0.1, 0.3, 0.2])
     # uneven shards on purpose (padding path): rank r owns [cuts[r], cuts[r+1])
     cuts = [0] + [int(P * (r + 1) / world) - (7 * (r + 1) if r + 1 < world else 0) for r in range(world)]

@@ -169,13 +169,14 @@ def test_debug_flag_and_repeat_calls():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_two_gpus_equals_single_gpu():
+@pytest.mark.parametrize("mode", ["all", "color_alpha"])
+def test_sharded_two_gpus_equals_single_gpu(mode):
     """Gaussian-index shards + tile-row windows over NCCL reproduce the single-GPU operator exactly."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multigpu_check.py"), "150000"]
+           "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multigpu_check.py"), "150000", mode]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MULTIGPU_CHECK OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
