@@ -367,6 +367,28 @@ SURFEL_API int surfel_adam_step(int n_groups, const surfel_adam_group *groups, d
 SURFEL_API int surfel_densification_stats(int P, const int *radii, const float *viewspace_grad, float *max_radii2D,
                                           float *xyz_gradient_accum, float *denom, void *stream);
 
+/*
+ * ---------------------------------------------------------------------------------------------
+ * Fused parameter activations and SH packing -- the caller-side row in front of the projection kernel.
+ * Reference: the GaussianModel properties every render() evaluates (scene/gaussian_model.py:31-39,101-127):
+ *   get_scaling = exp(_scaling) [P,2];  get_rotation = normalize(_rotation) [P,4] (x / max(||x||, 1e-12));
+ *   get_opacity = sigmoid(_opacity) [P,1];  get_features = cat((_features_dc [P,1,3], _features_rest [P,R,3]), 1)
+ * and their autograd (~12 PyTorch kernels forward, ~15 backward, two of them copies of the whole SH block).
+ * One launch each way.  sh_rest = R; features / g_features may be NULL (activations only); when given, the packed block
+ * must be 16-byte aligned.  The backward takes the ACTIVATED scaling / opacity
+ * (the forward's outputs) and the raw quaternion.
+ * ---------------------------------------------------------------------------------------------
+ */
+SURFEL_API int surfel_activate_forward(int P, int sh_rest, const float *scaling_raw, const float *rotation_raw,
+                                       const float *opacity_raw, const float *features_dc,
+                                       const float *features_rest, float *scaling, float *rotation, float *opacity,
+                                       float *features, void *stream);
+SURFEL_API int surfel_activate_backward(int P, int sh_rest, const float *rotation_raw, const float *scaling,
+                                        const float *opacity, const float *g_scaling, const float *g_rotation,
+                                        const float *g_opacity, const float *g_features, float *d_scaling_raw,
+                                        float *d_rotation_raw, float *d_opacity_raw, float *d_features_dc,
+                                        float *d_features_rest, void *stream);
+
 /* Test hook for the hand-written stable LSD radix sort used by the binning stage: sorts n
  * (uint32 key, uint32 value) pairs on key bits [0, end_bit) into the *_out arrays (device pointers). */
 SURFEL_API int surfel_debug_sort_pairs(int64_t n, int end_bit, const uint32_t *keys_in, const uint32_t *vals_in,

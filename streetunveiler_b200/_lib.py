@@ -61,6 +61,8 @@ SIGNATURES = {
     "surfel_loss_training_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "surfel_loss_training_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp]),
+    "surfel_activate_forward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_activate_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_adam_step": (_i, [_i, _vp, C.c_double, C.c_double, C.c_double, _vp]),
     "surfel_densification_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_sort_pairs": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -4,10 +4,12 @@ parameters and the optimiser step (train.py:109-199 without data loading, the sk
     activations (gaussian_model.py:107-127)  ->  rasterizer  ->  render() epilogue  ->  loss block  ->  backward
     ->  densification statistics  ->  Adam step
 
-Arm "fused":      this repo's rasterizer + fused epilogue (8f row 1) + fused loss (row 3) + fused update (row 4)
+Arm "fused":      fused activations + this repo's rasterizer + fused epilogue (8f row 1) + fused loss (row 3) + fused
+                  update (row 4)
 Arm "reference":  the UNMODIFIED reference extension (oracle/_ref; falls back to this repo's rasterizer if it is not
                   built, and says so) + the same steps as the PyTorch ops the reference runs.
-Both arms use the identical torch ops for the model's activations.  GPU box only."""
+The "reference" and "mixed" arms use the torch ops of scene/gaussian_model.py:101-127 for the model's activations.
+GPU box only."""
 import json, math, os, sys
 from types import SimpleNamespace
 import torch
@@ -19,6 +21,7 @@ from adam_cases import LRS
 from streetunveiler_b200 import synthetic as syn
 from streetunveiler_b200.fused_adam import FusedAdam, densification_stats
 from streetunveiler_b200.loss_block import training_loss
+from streetunveiler_b200.parameter_activation import activate
 from streetunveiler_b200.surface_epilogue import render_epilogue
 from test_adam_gpu import torch_stats
 from test_epilogue_gpu import torch_epilogue, view_of
@@ -44,10 +47,8 @@ def make_model():
 
 def iteration(arm, params, opt, stats):
     mod = arm["mod"]
-    # gaussian_model.py:107-127 (identical torch ops in both arms)
-    scaling, rotation = torch.exp(params["scaling"]), torch.nn.functional.normalize(params["rotation"])
-    opacity = torch.sigmoid(params["opacity"])
-    features = torch.cat((params["f_dc"], params["f_rest"]), dim=1)
+    scaling, rotation, opacity, features = arm["activate"](params["scaling"], params["rotation"], params["opacity"],
+                                                            params["f_dc"], params["f_rest"])
     means2D = torch.zeros_like(params["xyz"], requires_grad=True) + 0
     means2D.retain_grad()
     st = hz._settings(mod, cam, torch.zeros(3), 3, 1.0, dev)
@@ -78,11 +79,15 @@ def bench(arm, n=10):
     return e0.elapsed_time(e1) / n, float(loss)
 
 
-fused = dict(mod=hz.ours_module(), epilogue=render_epilogue, loss=training_loss, stats=densification_stats, opt=FusedAdam)
+def torch_activate(s, q, o, dc, rest):   # scene/gaussian_model.py:101-127
+    return torch.exp(s), torch.nn.functional.normalize(q), torch.sigmoid(o), torch.cat((dc, rest), dim=1)
+
+
+fused = dict(activate=activate, mod=hz.ours_module(), epilogue=render_epilogue, loss=training_loss, stats=densification_stats, opt=FusedAdam)
 have_ref = hz.reference_available()
-ref = dict(mod=hz.reference_module() if have_ref else hz.ours_module(), epilogue=torch_epilogue, loss=torch_training_loss,
+ref = dict(activate=torch_activate, mod=hz.reference_module() if have_ref else hz.ours_module(), epilogue=torch_epilogue, loss=torch_training_loss,
            stats=torch_stats, opt=torch.optim.Adam)
-mixed = dict(mod=hz.ours_module(), epilogue=torch_epilogue, loss=torch_training_loss, stats=torch_stats, opt=torch.optim.Adam)
+mixed = dict(activate=torch_activate, mod=hz.ours_module(), epilogue=torch_epilogue, loss=torch_training_loss, stats=torch_stats, opt=torch.optim.Adam)
 t_f, l_f = bench(fused)
 t_r, l_r = bench(ref)
 t_m, l_m = bench(mixed)
