@@ -14,8 +14,9 @@ __global__ void __launch_bounds__(ACT_THREADS) activate_fwd_kernel(const Activat
         if (i < a.P) activate_one(a, i);
         return;
     }
-    const long long t = (long long)(blockIdx.x - act_blocks) * ACT_THREADS + threadIdx.x;
-    if (4 * t < (long long)a.P * a.F) pack_features_word(a, t);   // the last word may be partial
+    // block b of the packing part covers words [b * ACT_THREADS * ACT_UNROLL, ...): thread x takes x, x + 256, x + 512, ...
+    const long long t = (long long)(blockIdx.x - act_blocks) * (ACT_THREADS * ACT_UNROLL) + threadIdx.x;
+    pack_features_words(a, t, ACT_THREADS);
 }
 
 __global__ void __launch_bounds__(ACT_THREADS) activate_bwd_kernel(const ActivateGradArgs a, const int act_blocks)
@@ -25,8 +26,8 @@ __global__ void __launch_bounds__(ACT_THREADS) activate_bwd_kernel(const Activat
         if (i < a.P) activate_grad_one(a, i);
         return;
     }
-    const long long t = (long long)(blockIdx.x - act_blocks) * ACT_THREADS + threadIdx.x;
-    if (4 * t < (long long)a.P * a.F) unpack_feature_grad_word(a, t);
+    const long long t = (long long)(blockIdx.x - act_blocks) * (ACT_THREADS * ACT_UNROLL) + threadIdx.x;
+    unpack_feature_grad_words(a, t, ACT_THREADS);
 }
 
 }  // namespace surfel
@@ -55,7 +56,7 @@ int surfel_activate_forward(int P, int sh_rest, const float *scaling_raw, const 
     const ActivateArgs a{P, F, scaling_raw, rotation_raw, opacity_raw, features_dc, features_rest, scaling, rotation, opacity, features};
     const int act_blocks = (P + ACT_THREADS - 1) / ACT_THREADS;
     const long long words = pack ? ((long long)P * F + 3) / 4 : 0;
-    const long long pack_blocks = (words + ACT_THREADS - 1) / ACT_THREADS;
+    const long long pack_blocks = (words + ACT_THREADS * ACT_UNROLL - 1) / (ACT_THREADS * ACT_UNROLL);
     if (act_blocks + pack_blocks > 0x7fffffffLL) return surfel_internal_fail(where, "too many elements for one launch");
     activate_fwd_kernel<<<(unsigned)(act_blocks + pack_blocks), ACT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, act_blocks);
     const cudaError_t e = cudaGetLastError();
@@ -81,7 +82,7 @@ int surfel_activate_backward(int P, int sh_rest, const float *rotation_raw, cons
                              d_scaling_raw, d_rotation_raw, d_opacity_raw, d_features_dc, d_features_rest};
     const int act_blocks = (P + ACT_THREADS - 1) / ACT_THREADS;
     const long long words = unpack ? ((long long)P * F + 3) / 4 : 0;
-    const long long pack_blocks = (words + ACT_THREADS - 1) / ACT_THREADS;
+    const long long pack_blocks = (words + ACT_THREADS * ACT_UNROLL - 1) / (ACT_THREADS * ACT_UNROLL);
     if (act_blocks + pack_blocks > 0x7fffffffLL) return surfel_internal_fail(where, "too many elements for one launch");
     activate_bwd_kernel<<<(unsigned)(act_blocks + pack_blocks), ACT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, act_blocks);
     const cudaError_t e = cudaGetLastError();

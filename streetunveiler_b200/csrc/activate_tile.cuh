@@ -71,48 +71,69 @@ __host__ __device__ inline void activate_grad_one(const ActivateGradArgs &a, con
     for (int c = 0; c < 4; c++) a.d_rotation_raw[4 * i + c] = g[c] / d - x[c] * k;
 }
 
-// Four consecutive floats of the packed [P, F] SH block (t = index of the 128-bit word): gather from dc / rest.
-__host__ __device__ inline void pack_features_word(const ActivateArgs &a, const long long t)
+// The packed [P, F] SH block is moved as 128-bit words: gather from dc / rest forward, scatter the gradient backward.
+// ACT_UNROLL words per thread, `stride` words apart (coalesced across the warp), all loads issued before the first
+// store so that several 128-bit transactions per thread are in flight.
+constexpr int ACT_UNROLL = 4;
+
+__host__ __device__ inline void pack_features_words(const ActivateArgs &a, const long long t, const long long stride)
 {
-    const long long e0 = 4 * t;
-    long long i = e0 / a.F;
-    int j = (int)(e0 - i * a.F);
-    const int R3 = a.F - 3;
-    float v[4];
+    const long long total = (long long)a.P * a.F, R3 = a.F - 3;
+    float v[ACT_UNROLL][4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-        v[u] = i < a.P ? (j < 3 ? a.features_dc[3 * i + j] : a.features_rest[(long long)R3 * i + (j - 3)]) : 0.f;
-        if (++j == a.F) { j = 0; i++; }
+    for (int w = 0; w < ACT_UNROLL; w++) {
+        const long long e0 = 4 * (t + w * stride);
+        long long i = e0 / a.F;
+        int j = (int)(e0 - i * a.F);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            v[w][u] = (e0 + u < total) ? (j < 3 ? a.features_dc[3 * i + j] : a.features_rest[R3 * i + (j - 3)]) : 0.f;
+            if (++j == a.F) { j = 0; i++; }
+        }
     }
-    const long long total = (long long)a.P * a.F;
-    if (e0 + 4 <= total) {
-        *reinterpret_cast<float4 *>(a.features + e0) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {   // last, partial word when P * F is not a multiple of 4
-        for (int u = 0; e0 + u < total; u++) a.features[e0 + u] = v[u];
+#pragma unroll
+    for (int w = 0; w < ACT_UNROLL; w++) {
+        const long long e0 = 4 * (t + w * stride);
+        if (e0 + 4 <= total) {
+            *reinterpret_cast<float4 *>(a.features + e0) = make_float4(v[w][0], v[w][1], v[w][2], v[w][3]);
+        } else {   // last, partial word when P * F is not a multiple of 4 (or nothing at all past the end)
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (e0 + u < total) a.features[e0 + u] = v[w][u];
+        }
     }
 }
 
-// ... and the reverse for the gradient: split 4 consecutive floats of dL/dfeatures into dL/ddc and dL/drest.
-__host__ __device__ inline void unpack_feature_grad_word(const ActivateGradArgs &a, const long long t)
+__host__ __device__ inline void unpack_feature_grad_words(const ActivateGradArgs &a, const long long t, const long long stride)
 {
-    const long long e0 = 4 * t, total = (long long)a.P * a.F;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (e0 + 4 <= total) {
-        const float4 g = *reinterpret_cast<const float4 *>(a.g_features + e0);
-        v[0] = g.x; v[1] = g.y; v[2] = g.z; v[3] = g.w;
-    } else {
-        for (int u = 0; e0 + u < total; u++) v[u] = a.g_features[e0 + u];
-    }
-    long long i = e0 / a.F;
-    int j = (int)(e0 - i * a.F);
-    const int R3 = a.F - 3;
+    const long long total = (long long)a.P * a.F, R3 = a.F - 3;
+    float v[ACT_UNROLL][4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-        if (i < a.P) {
-            if (j < 3) a.d_features_dc[3 * i + j] = v[u];
-            else a.d_features_rest[(long long)R3 * i + (j - 3)] = v[u];
+    for (int w = 0; w < ACT_UNROLL; w++) {
+        const long long e0 = 4 * (t + w * stride);
+        v[w][0] = v[w][1] = v[w][2] = v[w][3] = 0.f;
+        if (e0 + 4 <= total) {
+            const float4 g = *reinterpret_cast<const float4 *>(a.g_features + e0);
+            v[w][0] = g.x; v[w][1] = g.y; v[w][2] = g.z; v[w][3] = g.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (e0 + u < total) v[w][u] = a.g_features[e0 + u];
         }
-        if (++j == a.F) { j = 0; i++; }
+    }
+#pragma unroll
+    for (int w = 0; w < ACT_UNROLL; w++) {
+        const long long e0 = 4 * (t + w * stride);
+        long long i = e0 / a.F;
+        int j = (int)(e0 - i * a.F);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (e0 + u < total) {
+                if (j < 3) a.d_features_dc[3 * i + j] = v[w][u];
+                else a.d_features_rest[R3 * i + (j - 3)] = v[w][u];
+            }
+            if (++j == a.F) { j = 0; i++; }
+        }
     }
 }
 

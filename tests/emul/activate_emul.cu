@@ -12,7 +12,10 @@ __attribute__((visibility("default"))) void emul_activate_forward(int P, int sh_
 {
     const ActivateArgs a{P, 3 * (1 + sh_rest), scaling_raw, rotation_raw, opacity_raw, dc, rest, scaling, rotation, opacity, features};
     for (long long i = 0; i < P; i++) activate_one(a, i);
-    for (long long t = 0; 4 * t < (long long)P * a.F; t++) pack_features_word(a, t);
+    // the launch geometry of csrc/activate.cu: blocks of ACT_THREADS threads, ACT_UNROLL words per thread, ACT_THREADS apart
+    const long long words = ((long long)P * a.F + 3) / 4, per_block = (long long)ACT_THREADS * ACT_UNROLL;
+    for (long long b = 0; b * per_block < words; b++)
+        for (int x = 0; x < ACT_THREADS; x++) pack_features_words(a, b * per_block + x, ACT_THREADS);
 }
 
 __attribute__((visibility("default"))) void emul_activate_backward(int P, int sh_rest, const float *rotation_raw, const float *scaling, const float *opacity,
@@ -23,7 +26,9 @@ __attribute__((visibility("default"))) void emul_activate_backward(int P, int sh
     const ActivateGradArgs a{P, 3 * (1 + sh_rest), rotation_raw, scaling, opacity, g_scaling, g_rotation, g_opacity, g_features,
                              d_scaling_raw, d_rotation_raw, d_opacity_raw, d_dc, d_rest};
     for (long long i = 0; i < P; i++) activate_grad_one(a, i);
-    for (long long t = 0; 4 * t < (long long)P * a.F; t++) unpack_feature_grad_word(a, t);
+    const long long words = ((long long)P * a.F + 3) / 4, per_block = (long long)ACT_THREADS * ACT_UNROLL;
+    for (long long b = 0; b * per_block < words; b++)
+        for (int x = 0; x < ACT_THREADS; x++) unpack_feature_grad_words(a, b * per_block + x, ACT_THREADS);
 }
 
 }  // extern "C"

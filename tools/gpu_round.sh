@@ -20,6 +20,10 @@ if [ "$1" = "full" ]; then
   run bench_semantic python tools/bench_semantic.py
   run pcie python tools/pcie_probe.py
 fi
+if [ "$1" = "iteration-profile" ]; then
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file gpurun_out/r01_iteration_launches.csv python tools/bench_iteration.py > gpurun_out/ncu_iteration.log 2>&1; echo "ncu iteration rc=$?"
+  timeout 200 ncu --set full --clock-control none --import-source on -k regex:activate_ -c 2 -o gpurun_out/r01f_activate -f python tools/bench_activation.py > gpurun_out/ncu_activate.log 2>&1; echo "ncu activate rc=$?"
+fi
 if [ "$1" = "full" ] || [ "$1" = "profile" ]; then
   # ncu passes (never a source of bench numbers): launch list of the benchmark step, full captures of the blend kernels
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
