@@ -215,7 +215,7 @@ def timed_loop(fn, steps, warmup, world, device):
     return ms / steps
 
 
-def measure_e2e(mod, wl, args, world, device, sharded=None):
+def _measure_e2e_once(mod, wl, args, world, device, sharded=None):
     """Same metric through the operator with HOST buffers: every step copies all inputs (parameters and
     upstream gradients) from pinned host memory to the device, runs fwd+bwd, and copies every output and
     gradient back to pinned host memory.  Steps are software-pipelined over two device buffer sets and
@@ -233,6 +233,7 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
     ev_out = [torch.cuda.Event() for _ in range(2)]
     out_host = [{}, {}]
     trace = [] if os.environ.get("BENCH_E2E_TRACE") else None   # diagnostics: per-phase device timestamps on stderr
+    done = []                                                   # one timing event per step: its results have left the device
 
     def mark(stream):
         e = torch.cuda.Event(enable_timing=True)
@@ -288,12 +289,14 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
                     out_host[k][name] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
                 out_host[k][name].copy_(v.detach(), non_blocking=True)
             ev_out[k].record(s_out)
+            done.append(mark(s_out))
             if trace is not None:
                 t["out1"] = mark(s_out)
                 trace.append(t)
 
     steps = max(4, args.steps)
-    for i in range(2):
+    WARM = 6   # untimed steps: the caching allocator needs a few rounds until three steps' outputs can be in flight
+    for i in range(WARM):
         one(i)
     # every timed step uploads exactly one set of inputs (the one for the step after it) and downloads one set of
     # results; the upload queued by the last warm-up step belongs to the first timed step
@@ -305,15 +308,19 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
     e0.record(cur)
     for s_ in (s_in, s_out):
         s_.wait_stream(cur)
-    for i in range(2, steps + 2):
+    for i in range(WARM, steps + WARM):
         one(i)
     for s_ in (s_in, s_out):
         cur.wait_stream(s_)
     e1.record(cur)
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / steps
+    # per-step completion intervals on the device timeline: a step far above the median means the run was disturbed
+    # (a host stall starves the pipeline, because every forward waits for the host to read num_rendered)
+    intervals = [done[j - 1].elapsed_time(done[j]) for j in range(WARM + 1, len(done))]
+    stats = {"median_step_ms": round(float(np.median(intervals)), 3), "worst_step_ms": round(float(max(intervals)), 3)}
     if trace:
-        for i, t in enumerate(trace[3:9]):   # early timed steps, milliseconds since the start of the timed region
+        for i, t in enumerate(trace[WARM + 1:WARM + 7]):   # early timed steps, milliseconds since the start of the timed region
             try:
                 print("e2e trace step", i + 1, {n: round(e0.elapsed_time(ev), 2) for n, ev in t.items()}, file=sys.stderr)
             except Exception as exc:   # diagnostics only
@@ -323,7 +330,28 @@ def measure_e2e(mod, wl, args, world, device, sharded=None):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
     d2h = sum(v.numel() * v.element_size() for v in out_host[0].values())
-    return ms, int(h2d), int(d2h)
+    return ms, int(h2d), int(d2h), stats
+
+
+def measure_e2e(mod, wl, args, world, device, sharded=None):
+    """-> (ms per step, h2d bytes, d2h bytes, info).  Like the clock check of the device-resident loop, a disturbed run
+    is re-measured ONCE: if some step of the timed region took more than 3x the median step (all ranks agree on the
+    decision), the whole measurement is repeated and the faster of the two is reported, with both recorded in `info`."""
+    ms, h2d, d2h, stats = _measure_e2e_once(mod, wl, args, world, device, sharded)
+    info = dict(stats, remeasured=False)
+    disturbed = stats["worst_step_ms"] > 3.0 * stats["median_step_ms"]
+    if world > 1:
+        f = torch.tensor([1 if disturbed else 0], device=device)
+        torch.distributed.all_reduce(f, op=torch.distributed.ReduceOp.MAX)
+        disturbed = bool(int(f.item()))
+    if disturbed:
+        ms2, _, _, stats2 = _measure_e2e_once(mod, wl, args, world, device, sharded)
+        info = {"remeasured": True, "first_run": dict(stats, ms_per_step=round(ms, 3)),
+                "second_run": dict(stats2, ms_per_step=round(ms2, 3)),
+                "median_step_ms": stats2["median_step_ms"] if ms2 <= ms else stats["median_step_ms"],
+                "worst_step_ms": stats2["worst_step_ms"] if ms2 <= ms else stats["worst_step_ms"]}
+        ms = min(ms, ms2)
+    return ms, h2d, d2h, info
 
 
 def cpu_oracle_baseline(wl_host, cam, grads_host, threads=None):
@@ -370,7 +398,7 @@ def run_ours(args):
         print("debug: R after timed loop", state["R"], file=sys.stderr)
 
     # ---- e2e: host (pinned) buffers in, results out, every step ----
-    ms_e2e, h2d, d2h = measure_e2e(mod, wl, args, world, device, sharded)
+    ms_e2e, h2d, d2h, e2e_info = measure_e2e(mod, wl, args, world, device, sharded)
     if os.environ.get("BENCH_DEBUG"):
         print("debug: R after e2e loop", state["R"], file=sys.stderr)
 
@@ -428,7 +456,7 @@ def run_ours(args):
                    "l2": "per-GPU inputs (232 B/surfel, 464 MB at 2M) larger than the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3)},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3), "step_stats": e2e_info},
         "gpu_launches": HAND_WRITTEN_LAUNCHES_PER_STEP * args.steps,
         "gpu_launches_note": "per step: preprocess_fwd, 6 radix-sort passes x 3 kernels, 3 scan kernels, publish_u32, "
                              "emit_instances, tile_ranges, order_tiles, render_fwd, aux_zero_scan, 2 render_bwd "
@@ -465,9 +493,9 @@ def run_reference(args, force_cpu=False):
         ms_step = timed_loop(step, args.steps, args.warmup, 1, device)
         clocks = sampler.stop()
         value = wl.P / (ms_step * 1e-3) / 1e6
-        ms_e2e, h2d, d2h = measure_e2e(hz.reference_module(), wl, args, 1, device)
+        ms_e2e, h2d, d2h, e2e_info = measure_e2e(hz.reference_module(), wl, args, 1, device)
         e2e = {"value": round(wl.P / (ms_e2e * 1e-3) / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 3),
+               "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e, 3), "step_stats": e2e_info,
                "note": "the reference is a CUDA extension too, so its host-buffer call needs the same PCIe copies as ours; "
                        "device-resident throughput is `value`"}
         kind, cores = "reference", 0
