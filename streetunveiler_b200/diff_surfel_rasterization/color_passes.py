@@ -12,7 +12,6 @@ through the ``surfel_pass_*`` entry points of the C ABI.  There is no fallback: 
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import List, Optional, Sequence
 
 import torch

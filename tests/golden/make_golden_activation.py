@@ -11,7 +11,6 @@ import sys
 import types
 
 import numpy as np
-import torch
 from torch import nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))

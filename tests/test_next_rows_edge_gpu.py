@@ -1,7 +1,6 @@
 """Edge cases of the "next" rows on the GPU: empty and fully culled scenes, tiny images, degenerate
 optimiser groups, debug mode -- the situations the reference's callers can produce (densification can empty a semantic
 subset; a camera can look away from everything)."""
-import numpy as np
 import pytest
 import torch
 from torch import nn

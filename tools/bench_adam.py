@@ -4,7 +4,7 @@ import torch
 from torch import nn
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-from adam_cases import GROUPS, LRS, SHAPES
+from adam_cases import GROUPS, SHAPES
 from test_adam_gpu import torch_stats, fused_stats, make_optimizer
 from streetunveiler_b200.fused_adam import FusedAdam
 

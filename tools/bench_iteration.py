@@ -10,8 +10,7 @@ Arm "reference":  the UNMODIFIED reference extension (oracle/_ref; falls back to
                   built, and says so) + the same steps as the PyTorch ops the reference runs.
 The "reference" and "mixed" arms use the torch ops of scene/gaussian_model.py:101-127 for the model's activations.
 GPU box only."""
-import json, math, os, sys
-from types import SimpleNamespace
+import json, os, sys
 import torch
 from torch import nn
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
