@@ -260,6 +260,7 @@ def _measure_e2e_once(mod, wl, args, world, device, sharded=None):
         return t
 
     pending = {}
+    held = [None, None]
 
     def one(i):
         # step i: its inputs were queued by the previous call (or the prologue); queue the NEXT step's upload first, so
@@ -273,11 +274,14 @@ def _measure_e2e_once(mod, wl, args, world, device, sharded=None):
             s_comp.wait_event(ev_out[k])         # its previous results have left the device
             if trace is not None:
                 t["c0"] = mark(s_comp)
+            held[k] = None                        # ... so the device memory of those results may be reused from here on
             st = step()
             outs = {"color": st["color"], "allmap": st["allmap"], "radii": st["radii"], "g_means2D": m2.grad}
             outs.update({"g_" + name: v.grad for name, v in leaves.items()})
-            for v in outs.values():
-                v.record_stream(s_out)
+            # keep this step's results alive until the next step on this buffer set has waited for their download
+            # (instead of Tensor.record_stream, which defers the allocator's reuse by an unpredictable number of steps
+            # and makes it grow the pool -- multi-ms cudaMallocs -- in the middle of the timed region)
+            held[k] = outs
             ev_comp[k].record(s_comp)
             if trace is not None:
                 t["c1"] = mark(s_comp)
