@@ -65,3 +65,10 @@ def test_class_pass_validates_before_touching_the_device():
         rasterize_class_probabilities(s, z, z, torch.zeros(4, 1), lab, torch.zeros(9), **kw)
     with pytest.raises(RuntimeError, match="labels"):
         rasterize_class_probabilities(s, z, z, torch.zeros(4, 1), lab, torch.zeros(6), **kw)   # CPU labels: no fallback
+
+
+def test_training_step_surface():
+    from streetunveiler_b200.training import fused_training_step
+    params = list(inspect.signature(fused_training_step).parameters)
+    assert params[:7] == ["gaussians", "viewpoint_cam", "pipe", "background", "gt_image", "sky_image", "lambda_dssim"]
+    assert {"optimizer", "update_densification_stats", "lambda_normal", "lambda_dist"} <= set(params)

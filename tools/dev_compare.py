@@ -1,8 +1,6 @@
 """Development script (GPU box): ours vs reference extension vs oracle, plus quick timings."""
-import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
