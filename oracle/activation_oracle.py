@@ -27,7 +27,10 @@ def forward(scaling_raw, rotation_raw, opacity_raw, features_dc, features_rest):
 def backward(scaling_raw, rotation_raw, opacity_raw, g):
     """g: upstream gradients of the four outputs -> gradients of the five raw parameters."""
     s, q, o = (np.asarray(a, np.float64) for a in (scaling_raw, rotation_raw, opacity_raw))
-    y = 1.0 / (1.0 + np.exp(-o))
+    # autograd multiplies by the SAVED fp32 outputs (ExpBackward: grad * result; SigmoidBackward: grad * (1 - y) * y), so
+    # 1 - y carries the rounding of a saturated fp32 sigmoid -- restated here, not "improved"
+    y = (1.0 / (1.0 + np.exp(-o))).astype(np.float32).astype(np.float64)
+    e = np.exp(s).astype(np.float32).astype(np.float64)
     n = np.sqrt((q * q).sum(1, keepdims=True))
     d = np.maximum(n, EPS)
     gq = np.asarray(g["rotation"], np.float64)
@@ -35,5 +38,5 @@ def backward(scaling_raw, rotation_raw, opacity_raw, g):
     with np.errstate(divide="ignore", invalid="ignore"):
         k = np.where((n >= EPS) & (n > 0), dot / (d * d * n), 0.0)
     gf = np.asarray(g["features"], np.float64)
-    return {"scaling_raw": np.asarray(g["scaling"], np.float64) * np.exp(s), "rotation_raw": gq / d - q * k,
+    return {"scaling_raw": np.asarray(g["scaling"], np.float64) * e, "rotation_raw": gq / d - q * k,
             "opacity_raw": np.asarray(g["opacity"], np.float64) * (1.0 - y) * y, "features_dc": gf[:, :1], "features_rest": gf[:, 1:]}

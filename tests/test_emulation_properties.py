@@ -8,7 +8,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 
 import harness as hz
 
-COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+COMMON = dict(deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 
 
 def ptr(a):
@@ -92,5 +92,12 @@ def test_activation_code_matches_oracle_on_random_sizes(emul, P, R, seed):
                                 ptr(up["opacity"]), ptr(up["features"]), *[ptr(a) for a in grads])
     refg = ao.backward(raw[0], raw[1], raw[2], up)
     for a, k in zip(grads, ["scaling_raw", "rotation_raw", "opacity_raw", "features_dc", "features_rest"]):
-        if a.size:
-            assert np.isfinite(a).all() and hz.rel_err(a, refg[k]) <= 5e-6, k
+        if not a.size:
+            continue
+        assert np.isfinite(a).all(), k
+        if k == "opacity_raw":
+            # grad * (1 - y) * y with the fp32 y: one ulp of a saturated sigmoid (6e-8) is a large RELATIVE change of 1 - y,
+            # in the kernel as in PyTorch -- bound the error by ulps of y, not by the size of the (tiny) result
+            assert (np.abs(a - refg[k]) <= 5e-6 * np.abs(refg[k]) + 2.5e-7 * np.abs(up["opacity"])).all()
+        else:
+            assert hz.rel_err(a, refg[k]) <= 5e-6, k
