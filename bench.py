@@ -9,15 +9,18 @@ A "step" is one forward + one backward of the rasterizer operator over one synth
   * N = 1 (default): BASELINE config 3 -- STREET(P=2,000,000, seed 1), CAM-A 1920x1280, SH degree 3,
     colour + alpha upstream gradients.
   * N > 1 (torchrun, one rank per GPU): weak scaling -- every rank owns 2,000,000 surfels (an index
-    shard) of one STREET(2,000,000*N) scene; projected records are all-gathered, every rank blends
-    its interleaved tile rows, images are all-reduced and gradient records reduce-scattered to the
-    owners (streetunveiler_b200/sharded.py).
+    shard) of one STREET(2,000,000*N) scene (streetunveiler_b200/sharded.py).  The same invocation then
+    (a) checks the sharded result against the unsharded operator on rank 0 (`parity_selfcheck`) and
+    (b) times BASELINE configs[4] -- ONE 8,000,000-surfel scene split over the N ranks, strong scaling --
+    next to the single-GPU time of the same scene measured on rank 0 (`config5_strong`).
   * --impl reference: the UNMODIFIED reference CUDA extension rebuilt for sm_100a (oracle/_ref), same
     inputs and timing protocol, on the same GPU; falls back to the CPU oracle port when that build
     is absent.  --impl reference-cpu forces the CPU oracle port (host cores).
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
 synchronize on both sides, max over ranks; inputs (>460 MB) are larger than the 126 MB L2.
+`ms_per_step` / `value` are the K timed steps as one bracket (the driver's contract); `ms_per_step_median`
+is the median of the K per-step intervals inside that bracket.
 """
 from __future__ import annotations
 
@@ -42,10 +45,33 @@ from streetunveiler_b200 import synthetic as syn  # noqa: E402
 METRIC = "M Gaussians/s fwd+bwd @1920x1280"
 UNIT = "MGaussians/s"
 P_PER_GPU = 2_000_000
-# preprocess_fwd, 6 radix passes x (histogram, row scan, scatter), 3 scan kernels, publish_u32 (num_rendered read-back),
-# emit_instances, tile_ranges, order_tiles, render_fwd, aux_zero_scan, render_bwd x 2 specialisations (one returns at
-# once), preprocess_bwd -- every one hand-written (no library kernels on the path)
-HAND_WRITTEN_LAUNCHES_PER_STEP = 1 + 6 * 3 + 3 + 1 + 1 + 1 + 1 + 1 + 1 + 2 + 1
+STRONG_TOTAL = 8_000_000   # BASELINE configs[4]
+
+
+def count_launches(step_fn, device):
+    """Kernel launches of ONE step, counted by CUPTI (torch.profiler): -> (ours, other, {name: n}).  `ours` are the
+    hand-written kernels of libsurfel_b200.so (namespace surfel::), `other` everything else on the device in that step
+    (PyTorch fills / copies of the harness, NCCL)."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize(device)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step_fn()
+        torch.cuda.synchronize(device)
+    names = {}
+    for ev in prof.events():
+        if getattr(ev, "device_type", None) is not None and "cuda" in str(ev.device_type).lower():
+            n = ev.name
+            if n.startswith("Memcpy") or n.startswith("Memset"):
+                continue
+            names[n] = names.get(n, 0) + 1
+    mine = lambda n: "surfel::" in n or "publish_u32_kernel" in n   # noqa: E731  (the latter sits in api.cu's anonymous namespace)
+    ours = sum(c for n, c in names.items() if mine(n))
+    other = sum(c for n, c in names.items() if not mine(n))
+    short = {}
+    for n, c in names.items():
+        k = n.split("(")[0].replace("void ", "")[:60]
+        short[k] = short.get(k, 0) + c
+    return ours, other, short
 
 
 # ------------------------------------------------------------------------------------------------
@@ -196,24 +222,26 @@ def make_step(mod, wl: Workload, sharded=None, own_buffers=False):
 
 
 def timed_loop(fn, steps, warmup, world, device):
+    """-> (ms per step over the whole K-step bracket, median of the K per-step intervals); both max over ranks."""
     for _ in range(warmup):
         fn()
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize(device)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    marks[0].record()
+    for i in range(steps):
         fn()
-    e1.record()
+        marks[i + 1].record()
     torch.cuda.synchronize(device)
-    ms = e0.elapsed_time(e1)
+    ms = marks[0].elapsed_time(marks[steps]) / steps
+    med = float(np.median([marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]))
     if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        t = torch.tensor([ms, med], device=device, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, med = float(t[0].item()), float(t[1].item())
         torch.distributed.barrier()
-    return ms / steps
+    return ms, med
 
 
 def _measure_e2e_once(mod, wl, args, world, device, sharded=None):
@@ -376,6 +404,133 @@ def cpu_oracle_baseline(wl_host, cam, grads_host, threads=None):
     return wl_host["means3D"].shape[0] / dt / 1e6, dt, oracle.num_threads()
 
 
+def config1_baseline(device=None, mod=None):
+    """BASELINE configs[0]: 10k surfels, 256x256, SH degree 0 -- the pure-PyTorch CPU alpha-blend (oracle/torch_cpu_blend.py,
+    checker/baseline infrastructure) timed on the host cores, and, when a device is given, this repo's operator on the
+    same inputs (median of 20 calls after 3 warm-up calls)."""
+    from oracle import torch_cpu_blend as tb
+    cam, scene = syn.cam_s(), syn.box_scene(10_000, 3, 0)
+    grads = syn.upstream_grads(cam.width, cam.height, "color_alpha")
+    tb.forward_backward(scene, cam, grads)                      # warm-up (thread pool, allocator)
+    times = [tb.forward_backward(scene, cam, grads)[1] for _ in range(2)]
+    dt = float(np.median(times))
+    out = {"value": round(10_000 / dt / 1e6, 6), "unit": UNIT, "cores": int(torch.get_num_threads()), "kind": "port",
+           "host_cpus": os.cpu_count(),
+           "sample": f"BASELINE configs[0] whole workload: BOX(P=10000, seed=3) CAM-S 256x256 SH0, colour+alpha grads, one "
+                     f"fwd+bwd of the pure-PyTorch CPU alpha-blend (autograd backward), {dt:.2f} s"}
+    if device is not None and mod is not None:
+        import harness as hz
+        st = hz._settings(mod, cam, torch.zeros(3), 0, 1.0, device)
+        rast = mod.GaussianRasterizer(st)
+        leaves = {k: scene[k].to(device).requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        g = (grads[0].to(device), grads[1].to(device))
+
+        def step():
+            for t in list(leaves.values()) + [m2]:
+                t.grad = None
+            color, radii, allmap = rast(means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"],
+                                        shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+            torch.autograd.backward([color, allmap], [g[0], g[1]])
+        _, med = timed_loop(step, 20, 3, 1, device)
+        out["this_repo_gpu_ms"] = round(med, 4)
+        out["this_repo_gpu_value"] = round(10_000 / (med * 1e-3) / 1e6, 3)
+    return out
+
+
+def workload_name(P_total, seed, world, strong=False):
+    base = f"STREET(P={P_total}, seed={seed}) CAM-A 1920x1280 SH3, grads colour+alpha; BASELINE configs[{4 if strong else 2}]"
+    if world > 1:
+        base += (f"; index shards of {P_total // world} surfels per GPU, screen-band exchange of projected records and "
+                 f"gradient records over NCCL/NVLink (streetunveiler_b200/sharded.py)")
+    return base
+
+
+def make_config(P_total, P_rank, seed, world, R, P_vis, crc, strong=False):
+    """One function for both arms, so that equal workloads give equal `config` dicts."""
+    return {"workload": workload_name(P_total, seed, world, strong), "P_total": P_total, "P_per_gpu": P_rank,
+            "parallelism": f"index-shard x{world}" if world > 1 else "single", "num_rendered": R, "visible": P_vis,
+            "input_crc32": crc,
+            "l2": "per-GPU inputs (232 B/surfel, 464 MB at 2M) larger than the 126 MB L2; no explicit flush"}
+
+
+def issue_roofline(kernel, ms_per_launch, clocks):
+    """Second roofline of the dominant kernel (the blend kernels are instruction-issue bound, not HBM bound): executed
+    warp instructions per launch (ncu `smsp__inst_executed.sum`, profiles/issue.json -- a property of kernel + workload,
+    not of the clock) / the LIVE duration of this run, against 148 SMs x 4 schedulers x 1 warp instruction per cycle."""
+    path = os.path.join(ROOT, "profiles", "issue.json")
+    try:
+        rec = json.load(open(path)).get(kernel)
+    except Exception:
+        rec = None
+    if not rec:
+        return None
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    peak = 148 * 4 * mhz * 1e6 / 1e9                      # G warp-instructions / s
+    achieved = rec["inst_executed"] / (ms_per_launch * 1e-3) / 1e9
+    return {"bound": "issue", "kernel": kernel, "achieved": round(achieved, 1), "peak": round(peak, 1),
+            "unit": "G warp-inst/s", "frac": round(achieved / peak, 4), "inst_per_launch": rec["inst_executed"],
+            "ncu_issue_active_pct": rec.get("issue_active_pct"), "source": rec.get("source")}
+
+
+def gather_union(wl, world, device):
+    """Every rank's shard, concatenated in rank order = the scene the sharded operator renders (on every rank)."""
+    out = {}
+    for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+        x = wl.dev[k].contiguous()
+        full = x.new_empty((world * x.shape[0],) + tuple(x.shape[1:]))
+        torch.distributed.all_gather_into_tensor(full, x)
+        out[k] = full
+    return out
+
+
+def selfcheck_and_single(mod, wl, sharded, world, rank, device, steps, warmup, time_single):
+    """Sharded fwd+bwd on all ranks, then the UNSHARDED operator on the same scene on rank 0: images must be
+    bit-identical (CRC32 of colour + allmap), rank 0's shard of every gradient within 1e-4 (max-abs relative).  With
+    `time_single` rank 0 also times the single-GPU step on that scene (the N=1 point of the strong-scaling curve)."""
+    import zlib
+    import harness as hz
+    step, leaves, m2, state = make_step(mod, wl, sharded)
+    st = step()
+    torch.cuda.synchronize(device)
+    sh_color, sh_allmap = st["color"].detach().clone(), st["allmap"].detach().clone()
+    sh_grads = {k: v.grad.detach().clone() for k, v in leaves.items()}
+    sh_grads["means2D"] = m2.grad.detach().clone()
+    union = gather_union(wl, world, device)
+    res = None
+    if rank == 0:
+        class _U:   # a Workload-shaped view of the union for make_step
+            pass
+        u = _U()
+        u.cam, u.device, u.dev, u.grads, u.P = wl.cam, device, union, wl.grads, union["means3D"].shape[0]
+        ustep, uleaves, um2, ustate = make_step(mod, u)
+        ust = ustep()
+        torch.cuda.synchronize(device)
+        same = bool(torch.equal(ust["color"], sh_color) and torch.equal(ust["allmap"], sh_allmap))
+        crc_sh = zlib.crc32(sh_allmap.cpu().numpy().tobytes(), zlib.crc32(sh_color.cpu().numpy().tobytes()))
+        crc_un = zlib.crc32(ust["allmap"].detach().cpu().numpy().tobytes(),
+                            zlib.crc32(ust["color"].detach().cpu().numpy().tobytes()))
+        P = wl.P
+        errs = {}
+        for k, v in uleaves.items():
+            errs[k] = hz.rel_err(sh_grads[k].cpu().numpy(), v.grad[:P].cpu().numpy())
+        errs["means2D"] = hz.rel_err(sh_grads["means2D"].cpu().numpy(), um2.grad[:P].cpu().numpy())
+        worst = max(errs.values()) if errs else 0.0
+        res = {"scene_surfels": int(u.P), "image_bit_identical": same, "image_crc32_sharded": crc_sh,
+               "image_crc32_single_gpu": crc_un, "grad_max_rel_err": {k: float(f"{v:.3e}") for k, v in errs.items()},
+               "num_rendered_single_gpu": int(ustate["R"] or 0), "tolerance": 1e-4,
+               "ok": bool(same and crc_sh == crc_un and worst <= 1e-4)}
+        if time_single:
+            ms1, med1 = timed_loop(ustep, steps, warmup, 1, device)
+            res["single_gpu_ms_per_step"] = round(ms1, 4)
+            res["single_gpu_ms_per_step_median"] = round(med1, 4)
+        del ustep, uleaves, um2, ustate, ust, u
+    del union, sh_color, sh_allmap, sh_grads
+    torch.cuda.empty_cache()
+    torch.distributed.barrier()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     rank, world, local = dist_env()
@@ -384,13 +539,16 @@ def run_ours(args):
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=device)
+        import datetime
+        torch.distributed.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(minutes=20))
     from streetunveiler_b200 import _lib
     import harness as hz
     mod = hz.ours_module()
 
+    strong_only = bool(args.total)
     P_total = (args.total // world) * world if args.total else P_PER_GPU * world
-    wl = Workload(P_total, 1 if (world == 1 and not args.total) else 2, world, rank, device)
+    seed = 1 if (world == 1 and not args.total) else 2
+    wl = Workload(P_total, seed, world, rank, device)
     sharded = None
     if world > 1:
         from streetunveiler_b200.sharded import ShardedRasterizer
@@ -400,10 +558,18 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_step = timed_loop(step, args.steps, args.warmup, world, device)
+    ms_step, ms_median = timed_loop(step, args.steps, args.warmup, world, device)
     clocks = sampler.stop() if rank == 0 else None
     if os.environ.get("BENCH_DEBUG"):
         print("debug: R after timed loop", state["R"], file=sys.stderr)
+
+    # ---- kernel launches of one step, counted by CUPTI ----
+    try:
+        n_ours, n_other, launch_names = count_launches(step, device)
+        launch_note = "counted with CUPTI (torch.profiler) over one step after the timed region, x steps"
+    except Exception as exc:   # no CUPTI on this box: say so instead of guessing
+        n_ours, n_other, launch_names = 0, 0, {}
+        launch_note = f"NOT COUNTED: torch.profiler unavailable ({type(exc).__name__}: {exc})"
 
     # ---- e2e: host (pinned) buffers in, results out, every step ----
     ms_e2e, h2d, d2h, e2e_info = measure_e2e(mod, wl, args, world, device, sharded)
@@ -425,6 +591,7 @@ def run_ours(args):
     P_vis = int((state["radii"] > 0).sum().item())
     HW = wl.cam.width * wl.cam.height
     peak, peak_src = measured_peaks()
+    roof_issue = None
     if stages:
         dom = max(stages, key=stages.get)
         ab = alg_bytes_stage(dom, wl.P, P_vis, R, HW)
@@ -438,14 +605,37 @@ def run_ours(args):
                 traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "alg_bytes_per_launch": int(ab), "ms_per_launch": round(stages[dom], 4)}
+                "alg_bytes_per_launch": int(ab), "ms_per_launch": round(stages[dom], 4),
+                "note": "the blend kernels are instruction-issue bound (ncu: DRAM < 2 % of peak); `roofline_issue` is the "
+                        "bound that explains their duration, this entry is the HBM fraction the contract asks for"}
+        roof_issue = issue_roofline(dom, stages[dom], clocks)
 
+    # ---- N > 1: sharded-vs-single parity self-check and BASELINE configs[4] (one 8M scene, strong scaling) ----
+    selfcheck, strong = None, None
+    phases = None
     if world > 1:
         from streetunveiler_b200 import sharded as _sh
+        selfcheck = {"weak_scene": selfcheck_and_single(mod, wl, sharded, world, rank, device, args.steps, args.warmup,
+                                                        time_single=strong_only)}
+        if not strong_only:
+            del step, leaves, m2, state
+            wl2 = Workload((STRONG_TOTAL // world) * world, 2, world, rank, device)
+            step2, leaves2, m22, state2 = make_step(mod, wl2, sharded)
+            ms2, med2 = timed_loop(step2, args.steps, args.warmup, world, device)
+            chk = selfcheck_and_single(mod, wl2, sharded, world, rank, device, args.steps, args.warmup, time_single=True)
+            selfcheck["strong_scene"] = chk
+            if rank == 0:
+                n1 = chk.get("single_gpu_ms_per_step")
+                strong = {"workload": workload_name(wl2.P * world, 2, world, strong=True), "P_total": wl2.P * world,
+                          "n_gpus": world, "ms_per_step": round(ms2, 4), "ms_per_step_median": round(med2, 4),
+                          "value": round(wl2.P * world / (ms2 * 1e-3) / 1e6, 2), "unit": UNIT, "scaling": "strong",
+                          "n1_ms_per_step": n1, "speedup_vs_n1": round(n1 / ms2, 3) if n1 else None,
+                          "n1_note": "single-GPU step of the SAME scene (the union of the ranks' shards), timed on rank 0 of "
+                                     "this run with the same steps/warmup while the other ranks wait"}
         if _sh.PHASE_MS and rank == 0:
             import statistics
-            print("shard phases, median ms per call (sync'd):",
-                  {k: round(statistics.median(v), 3) for k, v in _sh.PHASE_MS.items()}, file=sys.stderr)
+            phases = {k: round(statistics.median(v), 3) for k, v in _sh.PHASE_MS.items()}
+            print("shard phases, median ms per call (sync'd):", phases, file=sys.stderr)
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if rank != 0:
@@ -454,33 +644,50 @@ def run_ours(args):
     step_bytes = alg_bytes_step(wl.P, R, HW)
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "ms_per_step_median": round(ms_median, 4),
+        "higher_is_better": True,
         "scaling": "strong" if args.total else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"STREET(P={P_total}, seed={1 if (world == 1 and not args.total) else 2}) CAM-A 1920x1280 SH3, "
-                               f"grads colour+alpha; BASELINE configs[2]" + ("" if world == 1 else
-                               f"; index shards of {P_PER_GPU} surfels per GPU, record all-gather + tile-row windows + image all-reduce + gradient reduce-scatter over NCCL"),
-                   "P_total": P_total, "P_per_gpu": wl.P, "parallelism": f"index-shard x{world}" if world > 1 else "single", "num_rendered": R, "visible": P_vis, "input_crc32": wl.crc,
-                   "l2": "per-GPU inputs (232 B/surfel, 464 MB at 2M) larger than the 126 MB L2; no explicit flush"},
+        "config": make_config(P_total, wl.P, seed, world, R, P_vis, wl.crc, strong=strong_only),
         "clocks": clocks,
         "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3), "step_stats": e2e_info},
-        "gpu_launches": HAND_WRITTEN_LAUNCHES_PER_STEP * args.steps,
-        "gpu_launches_note": "per step: preprocess_fwd, 6 radix-sort passes x 3 kernels, 3 scan kernels, publish_u32, "
-                             "emit_instances, tile_ranges, order_tiles, render_fwd, aux_zero_scan, 2 render_bwd "
-                             "specialisations (one returns at once), preprocess_bwd (sharded: +1 count_window_tiles, one "
-                             "render_bwd, no aux_zero_scan; memsets not counted); all hand-written, see "
-                             "profiles/r01_launches_final.md",
+        "gpu_launches": int(n_ours) * args.steps,
+        "gpu_launches_per_step": {"hand_written": int(n_ours), "other": int(n_other), "kernels": launch_names},
+        "gpu_launches_note": launch_note,
         "roofline": roof,
+        "roofline_issue": roof_issue,
         "step_roofline": {"alg_bytes": int(step_bytes), "achieved_gbs": round(step_bytes / (ms_step * 1e-3) / 1e9, 2),
                           "frac_of_peak": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),
                           "formula": "712 P + 36 R + 80 HW (SURVEY.md 8d)"},
         "stage_ms": {k: round(v, 4) for k, v in stages.items()},
     }
+    if selfcheck is not None:
+        line["parity_selfcheck"] = selfcheck
+    if strong is not None:
+        line["config5_strong"] = strong
+    if phases:
+        line["shard_phase_ms"] = phases
+    if world == 1 and not args.total and not args.no_strong:
+        # the N = 1 point of BASELINE configs[4]: the 8M scene on one GPU
+        del step, leaves, m2, state
+        torch.cuda.empty_cache()
+        wl8 = Workload(STRONG_TOTAL, 2, 1, 0, device)
+        step8, _l8, _m8, state8 = make_step(mod, wl8)
+        ms8, med8 = timed_loop(step8, max(5, args.steps // 2), args.warmup, 1, device)
+        line["config5_strong"] = {"workload": workload_name(STRONG_TOTAL, 2, 1, strong=True), "P_total": STRONG_TOTAL,
+                                  "n_gpus": 1, "ms_per_step": round(ms8, 4), "ms_per_step_median": round(med8, 4),
+                                  "value": round(STRONG_TOTAL / (ms8 * 1e-3) / 1e6, 2), "unit": UNIT, "scaling": "strong",
+                                  "num_rendered": int(state8["R"] or 0), "input_crc32": wl8.crc}
+        del step8, _l8, _m8, state8, wl8
     if world == 1 and not args.no_cpu_baseline:
         v, dt, th = cpu_oracle_baseline(wl.host, wl.cam, wl.grads_host)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": th, "kind": "port",
                                 "sample": f"whole workload (P={wl.P}), 1 step fwd+bwd of the C oracle, {dt:.1f} s"}
+        try:
+            line["cpu_baseline_config1"] = config1_baseline(device, mod)
+        except Exception as exc:
+            line["cpu_baseline_config1"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
     print(json.dumps(line))
 
 
@@ -491,6 +698,7 @@ def run_reference(args, force_cpu=False):
     import harness as hz
     use_gpu_ref = (not force_cpu) and torch.cuda.is_available() and hz.reference_available()
     cam = syn.cam_a()
+    P_vis = None
     if use_gpu_ref:
         device = torch.device("cuda", local)
         torch.cuda.set_device(device)
@@ -498,7 +706,7 @@ def run_reference(args, force_cpu=False):
         step, leaves, m2, state = make_step(hz.reference_module(), wl)
         sampler = ClockSampler(local)
         sampler.start()
-        ms_step = timed_loop(step, args.steps, args.warmup, 1, device)
+        ms_step, ms_median = timed_loop(step, args.steps, args.warmup, 1, device)
         clocks = sampler.stop()
         value = wl.P / (ms_step * 1e-3) / 1e6
         ms_e2e, h2d, d2h, e2e_info = measure_e2e(hz.reference_module(), wl, args, 1, device)
@@ -510,6 +718,7 @@ def run_reference(args, force_cpu=False):
         sample = ("UNMODIFIED reference CUDA extension (oracle/_ref, rebuilt for sm_100a) on the same GPU, whole "
                   "workload; the reference has no CPU implementation of this path")
         R = int(state["R"] or 0)
+        P_vis = int((state["radii"] > 0).sum().item())
         crc = wl.crc
     else:
         scene = syn.street_scene(P_PER_GPU, 1, 3)
@@ -520,16 +729,17 @@ def run_reference(args, force_cpu=False):
             v, dt, cores = cpu_oracle_baseline(scene, cam, grads)
             times.append(dt)
         ms_step = float(np.mean(times)) * 1e3
+        ms_median = float(np.median(times)) * 1e3
         value = P_PER_GPU / (ms_step * 1e-3) / 1e6
         kind, clocks, R = "port", None, None
         e2e = {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         sample = "C oracle port of the reference algorithm on all host threads, whole workload"
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
+        "ms_per_step_median": round(ms_median, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "STREET(P=2000000, seed=1) CAM-A 1920x1280 SH3, grads colour+alpha; BASELINE configs[2]",
-                   "num_rendered": R, "input_crc32": crc},
+        "config": make_config(P_PER_GPU, P_PER_GPU, 1, 1, R, P_vis, crc),
         "clocks": clocks,
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": e2e,
@@ -544,6 +754,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 8M-surfel configs[4] leg (quick runs)")
     ap.add_argument("--total", type=int, default=0,
                     help="strong scaling: total surfels split over the ranks (BASELINE configs[4]: --total 8000000); "
                          "default 0 = weak scaling with 2,000,000 surfels per GPU")

@@ -28,6 +28,12 @@
  *
  * The library keeps no state between calls: forward -> backward state lives in the three
  * caller-owned scratch buffers (geometry / binning / image), whose layout is private.
+ *
+ * Threading: every entry point may be called concurrently from several host threads (e.g. one per
+ * GPU or per stream) as long as no two calls share a scratch or output buffer.  The error message
+ * (`surfel_last_error`) and the pinned num_rendered read-back word are per host thread; the options
+ * of `surfel_set_option` are process-wide atomics (each call reads an option once); the optional
+ * stage clocks ("time_stages") are accumulated under a mutex and make every stage synchronise.
  */
 #ifndef SURFEL_RASTERIZER_H_INCLUDED
 #define SURFEL_RASTERIZER_H_INCLUDED
@@ -400,6 +406,12 @@ SURFEL_API int surfel_debug_sort_pairs(int64_t n, int end_bit, const uint32_t *k
 SURFEL_API int surfel_debug_copy_geometry(int P, const char *geometry_buffer, uint32_t *tiles_touched_out,
                                           uint32_t *idx_sorted_out, uint32_t *offsets_out, float *records_out,
                                           void *stream);
+
+/* Debug view of the backward's device-side decision (render_bwd.cu: aux_zero_scan_kernel): *flag_host (HOST int) = 1
+ * if the last surfel_backward / surfel_pass_backward_blend on this grad_scratch ran the full blend specialisation
+ * (some depth / normal / median-depth / distortion gradient was non-zero at a pixel that blended a splat), 0 if the
+ * colour+alpha one.  Synchronises the stream. */
+SURFEL_API int surfel_debug_aux_flag(int P, const char *grad_scratch, int *flag_host, void *stream);
 
 /* Tuning / debug knobs: "subtile_cull" (default 1), "time_stages" (default 0; setting it clears the
  * stage clocks).  Returns 0 if the option exists. */

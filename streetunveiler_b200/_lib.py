@@ -67,6 +67,7 @@ SIGNATURES = {
     "surfel_densification_stats": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_sort_pairs": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "surfel_debug_copy_geometry": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_debug_aux_flag": (_i, [_i, _vp, C.POINTER(_i), _vp]),
     "surfel_set_option": (_i, [C.c_char_p, _i]),
     "surfel_stage_count": (_i, []),
     "surfel_stage_name": (C.c_char_p, [_i]),

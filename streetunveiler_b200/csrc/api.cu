@@ -3,8 +3,10 @@
 // Mirrors the raw-pointer layer CudaRasterizer::Rasterizer::{forward,backward,markVisible}
 // (RAST/cuda_rasterizer/rasterizer.h:24-86; orchestration rasterizer_impl.cu:198-342,346-448)
 // with caller-owned memory, an explicit stream and int error codes.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "../../include/surfel_rasterizer.h"
@@ -15,15 +17,19 @@ using namespace surfel;
 
 namespace {
 
+// Threading contract (stated in include/surfel_rasterizer.h): every entry point may be called concurrently from
+// several host threads (one per GPU / stream).  Error text and the read-back slot are per thread; the options are
+// process-wide atomics (a call reads each of them once); the optional stage clocks are guarded by a mutex.
 thread_local std::string g_err;
-int g_subtile_cull = 1;
-int g_bwd_variant = 2;  // see launch_render_bwd
+std::atomic<int> g_subtile_cull{1};
+std::atomic<int> g_bwd_variant{2};  // see launch_render_bwd
 
 // ---- optional per-stage device timing (bench.py roofline measurement) ----
 constexpr int N_STAGES = 6;
 const char *const kStageNames[N_STAGES] = {"preprocess_fwd", "depth_order", "tile_binning",
                                            "render_fwd",     "render_bwd",  "preprocess_bwd"};
-int g_time_stages = 0;
+std::atomic<int> g_time_stages{0};
+std::mutex g_stage_mutex;
 double g_stage_ms[N_STAGES] = {0, 0, 0, 0, 0, 0};
 int g_stage_calls[N_STAGES] = {0, 0, 0, 0, 0, 0};
 
@@ -33,7 +39,7 @@ struct StageClock {  // brackets a stage with two events on the launching stream
     cudaEvent_t a = nullptr, b = nullptr;
     StageClock(cudaStream_t s, int id) : st(s), stage(id)
     {
-        if (!g_time_stages) return;
+        if (!g_time_stages.load(std::memory_order_relaxed)) return;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
         cudaEventRecord(a, st);
@@ -45,6 +51,7 @@ struct StageClock {  // brackets a stage with two events on the launching stream
         cudaEventSynchronize(b);
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(g_stage_mutex);
             g_stage_ms[stage] += ms;
             g_stage_calls[stage] += 1;
         }
@@ -298,6 +305,7 @@ const char *surfel_stage_name(int stage) { return (stage >= 0 && stage < N_STAGE
 int surfel_stage_time(int stage, double *total_ms, int *calls)
 {
     if (stage < 0 || stage >= N_STAGES || !total_ms || !calls) return fail("surfel_stage_time", "bad arguments");
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
     *total_ms = g_stage_ms[stage];
     *calls = g_stage_calls[stage];
     return 0;
@@ -316,6 +324,7 @@ int surfel_set_option(const char *name, int value)
         return 0;
     }
     if (name && std::strcmp(name, "time_stages") == 0) {  // (re)arms and clears the stage clocks
+        std::lock_guard<std::mutex> lock(g_stage_mutex);
         g_time_stages = value;
         for (int i = 0; i < N_STAGES; i++) { g_stage_ms[i] = 0; g_stage_calls[i] = 0; }
         return 0;
@@ -858,6 +867,18 @@ int surfel_debug_sort_pairs(int64_t n, int end_bit, const uint32_t *keys_in, con
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(temp);
     if (e != cudaSuccess) return fail_cuda("surfel_debug_sort_pairs", e);
+    return 0;
+}
+
+int surfel_debug_aux_flag(int P, const char *grad_scratch, int *flag_host, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P <= 0 || !grad_scratch || !flag_host) return fail("surfel_debug_aux_flag", "bad arguments");
+    char *gp = const_cast<char *>(grad_scratch);
+    carve<float>(gp, (size_t)P * GACC_FLOATS);
+    const int *flag = carve<int>(gp, 1);
+    CK("copy flag", cudaMemcpyAsync(flag_host, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK("copy flag", cudaStreamSynchronize(st));
     return 0;
 }
 

@@ -283,7 +283,7 @@ preprocess_fwd_kernel(const int P, const int D, const int M, const float *__rest
             float sh[48];
             const float *row = shs + (size_t)idx * M * 3;
             const int ncoef = (D + 1) * (D + 1);
-            if ((M & 3) == 0) {
+            if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {   // rows 16-B aligned: 128-bit loads
                 const float4 *row4 = reinterpret_cast<const float4 *>(row);
 #pragma unroll
                 for (int i = 0; i < 12; i++)

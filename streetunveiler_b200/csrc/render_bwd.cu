@@ -69,30 +69,38 @@ struct Butterfly {
 // (train.py enables those losses late; BASELINE configs 2, 3, 5): aux_zero_scan_kernel finds out on the device and
 // the launcher queues BOTH specialisations of the blend kernel -- AUX = true (all recurrences) and AUX = false
 // (colour + alpha only: 14 fewer live values per pixel) -- each of which returns at once unless the flag selects it.
-// No host round trip; the cost is one pass over six gradient planes (~15 us) and one empty launch (~9 us).
-__global__ void __launch_bounds__(256) aux_zero_scan_kernel(const float *__restrict__ dL_dothers, const size_t HW,
+// No host round trip; the cost is one pass over six gradient planes + the contributor plane and one empty launch.
+// Only pixels that blended at least one splat count (n_contrib > 0): the blend kernel never reads the gradients of the
+// others, and the reference's caller puts NaN = 0/0 into dL/dallmap[0] exactly there (alpha == 0 pixels of
+// gaussian_renderer/__init__.py:158, e.g. sky), which must not force the full specialisation on every street frame.
+__global__ void __launch_bounds__(256) aux_zero_scan_kernel(const float *__restrict__ dL_dothers,
+                                                            const uint32_t *__restrict__ n_contrib, const size_t HW,
                                                             int *__restrict__ flag)
 {
     bool any = false;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
-    if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dothers) & 15) == 0) {
-        // channel 0 and channels 2..6 as 128-bit words, four independent loads in flight per thread
+    if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dothers) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(n_contrib) & 15) == 0) {
+        // four pixels per thread and step: one 128-bit word of n_contrib and of channels 0, 2..6 (1 = alpha is always
+        // consumed) -- seven independent loads in flight
         const float4 *v = reinterpret_cast<const float4 *>(dL_dothers);
-        const size_t q = HW / 4, n = 6 * q;
-        for (size_t i0 = tid; i0 < n; i0 += 4 * nthreads) {
-            float4 x[4];
+        const uint4 *nc = reinterpret_cast<const uint4 *>(n_contrib);
+        const size_t q = HW / 4;
+        for (size_t i = tid; i < q; i += nthreads) {
+            const uint4 c = nc[i];
+            float4 x[6];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const size_t i = i0 + u * nthreads;
-                x[u] = i < n ? v[i < q ? i : i + q] : make_float4(0.f, 0.f, 0.f, 0.f);   // skip channel 1 (alpha)
-            }
+            for (int u = 0; u < 6; u++) x[u] = v[i + (u == 0 ? 0 : (u + 1) * q)];
 #pragma unroll
-            for (int u = 0; u < 4; u++) any |= x[u].x != 0.f || x[u].y != 0.f || x[u].z != 0.f || x[u].w != 0.f;
+            for (int u = 0; u < 6; u++)
+                any |= (c.x != 0u && x[u].x != 0.f) || (c.y != 0u && x[u].y != 0.f) || (c.z != 0u && x[u].z != 0.f) ||
+                       (c.w != 0u && x[u].w != 0.f);
         }
     } else {
         for (size_t p = tid; p < HW; p += nthreads)
-            any |= dL_dothers[p] != 0.f || dL_dothers[2 * HW + p] != 0.f || dL_dothers[3 * HW + p] != 0.f ||
-                   dL_dothers[4 * HW + p] != 0.f || dL_dothers[5 * HW + p] != 0.f || dL_dothers[6 * HW + p] != 0.f;
+            any |= n_contrib[p] != 0u &&
+                   (dL_dothers[p] != 0.f || dL_dothers[2 * HW + p] != 0.f || dL_dothers[3 * HW + p] != 0.f ||
+                    dL_dothers[4 * HW + p] != 0.f || dL_dothers[5 * HW + p] != 0.f || dL_dothers[6 * HW + p] != 0.f);
     }
     if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;   // benign race: every writer stores 1
 }
@@ -396,7 +404,7 @@ void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
         return;
     }
     cudaMemsetAsync(a.aux_flag, 0, sizeof(int), stream);
-    aux_zero_scan_kernel<<<148 * 4, 256, 0, stream>>>(a.dL_dothers, (size_t)a.W * a.H, a.aux_flag);
+    aux_zero_scan_kernel<<<148 * 8, 256, 0, stream>>>(a.dL_dothers, a.n_contrib, (size_t)a.W * a.H, a.aux_flag);
     // 2 is the default (api.cu).  Measured at 2M surfels (tools/bench_variants.py, ms for colour+alpha | all gradients):
     // v0 3.14 | 3.49, v1 2.64 | 3.51, v2 2.63 | 3.42, v3 2.98 | 3.51, v4 3.12 | 3.85.
     switch (a.variant) {

@@ -18,6 +18,7 @@ NUM_CHANNELS = 3  # RAST/cuda_rasterizer/config.h:15
 # tests only: when KEEP_LAST is set, the scratch buffers of the most recent forward stay reachable here
 KEEP_LAST = False
 LAST = None
+LAST_BWD_AUX = None   # tests only (KEEP_LAST): 1 if the last backward ran the full blend specialisation, 0 if colour+alpha
 
 
 def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -132,6 +133,11 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                 _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D), _ptr(dL_dtransMat),
                 _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations), _ptr(scratch), _stream(), int(bool(debug))),
                 "surfel_backward")
+            if KEEP_LAST:
+                global LAST_BWD_AUX
+                flag = C.c_int(-1)
+                _lib.check(L.surfel_debug_aux_flag(P, _ptr(scratch), C.byref(flag), _stream()), "surfel_debug_aux_flag")
+                LAST_BWD_AUX = int(flag.value)
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations
 
 

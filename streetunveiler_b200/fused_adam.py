@@ -40,6 +40,7 @@ class FusedAdam(torch.optim.Optimizer):
         # one launch per distinct (betas, eps, device); the reference has exactly one
         batches = {}
         keep = []
+        stepped = []   # step counters advance only after every parameter validated and every launch succeeded
         for group in self.param_groups:
             for p in group["params"]:
                 if p.grad is None:
@@ -53,7 +54,6 @@ class FusedAdam(torch.optim.Optimizer):
                     state["step"] = torch.tensor(0.0, dtype=torch.float32)
                     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                state["step"] += 1
                 m, v = state["exp_avg"], state["exp_avg_sq"]
                 if m.shape != p.shape or v.shape != p.shape or not m.is_contiguous() or not v.is_contiguous():
                     raise RuntimeError("optimizer state does not match its parameter")
@@ -64,7 +64,8 @@ class FusedAdam(torch.optim.Optimizer):
                 key = (group["betas"][0], group["betas"][1], group["eps"], p.device)
                 batches.setdefault(key, []).append(
                     _lib.AdamGroup(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(group["lr"]),
-                                   int(state["step"])))
+                                   int(state["step"]) + 1))
+                stepped.append(state)
         L = _lib.lib()
         for (b1, b2, eps, dev), items in batches.items():
             with torch.cuda.device(dev):
@@ -73,6 +74,8 @@ class FusedAdam(torch.optim.Optimizer):
                     part = items[i:i + _MAX_GROUPS]
                     arr = (_lib.AdamGroup * len(part))(*part)
                     _lib.check(L.surfel_adam_step(len(part), arr, float(b1), float(b2), float(eps), st), "surfel_adam_step")
+        for state in stepped:
+            state["step"] += 1
         del keep
         return loss
 
