@@ -69,7 +69,7 @@ def count_launches(step_fn, device):
     other = sum(c for n, c in names.items() if not mine(n))
     short = {}
     for n, c in names.items():
-        k = n.split("(")[0].replace("void ", "")[:60]
+        k = n.replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "")[:60]
         short[k] = short.get(k, 0) + c
     return ours, other, short
 

@@ -155,21 +155,29 @@ SURFEL_API int surfel_debug_copy_binning(int width, int height, int64_t num_rend
 
 /*
  * ---------------------------------------------------------------------------------------------
- * Sharded (multi-GPU) path -- not part of the reference, which is single-GPU only.
- * Gaussians are sharded by index across ranks; the screen is partitioned by tile rows
- * ("window": rows y with y >= row_offset and (y - row_offset) % row_stride == 0).  Call sequence
- * per rank (host side: streetunveiler_b200/sharded.py):
- *   surfel_shard_preprocess   own shard -> projected records [P,24] fp32, radii, depth keys, clamp bytes
- *   surfel_shard_compact      keep the rows that survived culling (radius > 0), index order preserved;
- *                             slot[i] = compact row of Gaussian i.  Only these rows are exchanged.
- *   (all-gather of compact records / radii / depth keys over NCCL, padded to the largest count)
- *   surfel_window_prepare     depth order of ALL gathered Gaussians, instance count of the own window
- *   surfel_window_render      binning + blend of the own tile rows into full-size image planes
- *   (all-gather of the image rows)
- *   surfel_window_backward    gradient records [P_total,20] of the own tile rows (zeroed by the call)
- *   (reduce-scatter of the gradient records to the owners of the Gaussians)
- *   surfel_shard_backward     own shard: gradient record (row slot[i] if grad_slot is given) -> parameter gradients
- * Every per-pixel result is identical to the single-GPU path (same lists, same order).
+ * Sharded (multi-GPU) path -- not part of the reference, which is single-GPU only
+ * (/root/reference/utils/general_utils.py:133).  Gaussians are sharded by index across G ranks; the SCREEN is
+ * partitioned into G contiguous ranges of row-major tile ids ("window" = tiles [tile_lo, tile_hi)), cut so that
+ * every range holds the same share of the frame's (tile, Gaussian) instances, and a projected record travels only
+ * to the ranks whose range its tile rect touches.  Call sequence per rank (host side and the collectives:
+ * streetunveiler_b200/sharded.py):
+ *   surfel_shard_preprocess     own shard -> projected records [P,24] fp32, radii, depth keys, clamp bytes
+ *   surfel_shard_tile_hist      instances per tile of the own shard        (all-reduce(sum) -> global histogram)
+ *   surfel_shard_partition      global histogram -> cuts[G+1] (tile ranges) and the exact instance count of every range
+ *   surfel_shard_route_count    per-destination send counts                (all-gather -> counts matrix; ONE host sync)
+ *   surfel_shard_route_scatter  112-B rows (record, depth key, radius) into per-destination segments, index order kept
+ *   (all-to-all of the rows)
+ *   surfel_window_unpack        received rows -> records / radii / depth keys
+ *   surfel_window_prepare       depth order of the received Gaussians, instance offsets of the own window
+ *   surfel_window_render        binning + blend of the own tiles into full-size image planes (other tiles untouched)
+ *   (all-reduce(sum) of the image planes: every pixel has exactly one non-zero summand)
+ *   surfel_window_backward      gradient rows [n_received,20] of the own tiles (zeroed by the call)
+ *   (all-to-all of the gradient rows back along the same routes)
+ *   surfel_shard_grad_accumulate  returned rows summed into the per-Gaussian accumulator [P,20]
+ *   surfel_shard_backward       own shard: accumulator row -> parameter gradients
+ * Every per-pixel result is identical to the single-GPU path (same lists, same order); upstream gradients must be
+ * the same on every rank (each rank back-propagates only its own tiles).
+ * surfel_shard_compact / the (records, radii, keys) all-gather scheme of round 1 remain available.
  * ---------------------------------------------------------------------------------------------
  */
 SURFEL_API int surfel_shard_preprocess(
@@ -187,18 +195,41 @@ SURFEL_API int surfel_shard_compact(
     int P, const int *radii, const float *records, const uint32_t *depth_keys,
     float *records_c, int *radii_c, uint32_t *depth_keys_c, uint32_t *slot, int *count_dev,
     char *temp, void *stream);
+/* hist: uint32[tiles] (tiles = ceil(W/16) * ceil(H/16)), overwritten. */
+SURFEL_API int surfel_shard_tile_hist(int P, int width, int height, const float *records, const int *radii,
+                                      uint32_t *hist, void *stream);
+/* hist: the all-reduced histogram.  cost of a tile = its instance count + cost_base.  cuts: DEVICE int32[G+1],
+ * window_num_rendered: DEVICE int64[G]; temp: surfel_shard_partition_bytes(width, height).  1 <= G <= 16. */
+SURFEL_API size_t surfel_shard_partition_bytes(int width, int height);
+SURFEL_API int surfel_shard_partition(int width, int height, int G, const uint32_t *hist, int cost_base, char *temp,
+                                      int *cuts, int64_t *window_num_rendered, void *stream);
+/* temp: surfel_shard_route_bytes(P, G), shared by the two calls.  send_counts: DEVICE int32[G].
+ * send_rows: [sum(send_counts), 28] fp32, segment d = rows for rank d; send_src[row] = local Gaussian index. */
+SURFEL_API size_t surfel_shard_route_bytes(int P, int G);
+SURFEL_API int surfel_shard_route_count(int P, int width, int height, int G, const float *records, const int *radii,
+                                        const int *cuts, char *temp, int *send_counts, void *stream);
+SURFEL_API int surfel_shard_route_scatter(int P, int G, const float *records, const int *radii,
+                                          const uint32_t *depth_keys, char *temp, const int *send_counts,
+                                          float *send_rows, uint32_t *send_src, void *stream);
+SURFEL_API int surfel_window_unpack(int n, const float *rows, float *records, int *radii, uint32_t *depth_keys,
+                                    void *stream);
+/* grad_records [P,20] is zeroed, then grad_records[send_src[j]] += grad_rows[j] for j < n_rows. */
+SURFEL_API int surfel_shard_grad_accumulate(int P, int64_t n_rows, const float *grad_rows, const uint32_t *send_src,
+                                            float *grad_records, void *stream);
 SURFEL_API size_t surfel_window_bytes(int P_total);
+/* num_rendered (HOST) may be NULL when the caller already knows the window's instance count (surfel_shard_partition):
+ * then the call does not synchronise. */
 SURFEL_API int surfel_window_prepare(
-    int P_total, int width, int height, int row_offset, int row_stride,
+    int P_total, int width, int height, int tile_lo, int tile_hi,
     const float *records, const int *radii, const uint32_t *depth_keys,
     char *window_buffer, int64_t *num_rendered, void *stream, int debug);
 SURFEL_API int surfel_window_render(
-    int P_total, int width, int height, int row_offset, int row_stride, int64_t num_rendered,
+    int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
     const float *background, const float *records, const int *radii,
     char *window_buffer, char *binning_buffer, char *image_buffer,
     float *out_color, float *out_others, void *stream, int debug);
 SURFEL_API int surfel_window_backward(
-    int P_total, int width, int height, int row_offset, int row_stride, int64_t num_rendered,
+    int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
     const float *background, const float *records, char *binning_buffer, char *image_buffer,
     const float *dL_dpix, const float *dL_dothers, float *grad_records, void *stream, int debug);
 SURFEL_API int surfel_shard_backward(

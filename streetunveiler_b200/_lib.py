@@ -35,6 +35,14 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp]),
     "surfel_shard_compact_bytes": (C.c_size_t, [_i]),
     "surfel_shard_compact": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_shard_tile_hist": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "surfel_shard_partition_bytes": (C.c_size_t, [_i, _i]),
+    "surfel_shard_partition": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "surfel_shard_route_bytes": (C.c_size_t, [_i, _i]),
+    "surfel_shard_route_count": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_shard_route_scatter": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_window_unpack": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_shard_grad_accumulate": (_i, [_i, _i64, _vp, _vp, _vp, _vp]),
     "surfel_window_bytes": (C.c_size_t, [_i]),
     "surfel_window_prepare": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _i]),
     "surfel_window_render": (_i, [_i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),

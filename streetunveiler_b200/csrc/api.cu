@@ -265,7 +265,7 @@ int bin_stage(int P, int width, int height, int64_t num_rendered, const int *rad
 {
     const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
     StageClock clk_bin(st, 2);
-    CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, 0, 1, g.rec, radii, g.idx_sorted, g.offsets,
+    CK("tile binning", run_tile_binning(P, num_rendered, gx, gy, 0, gx * gy, g.rec, radii, g.idx_sorted, g.offsets,
                                         bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted, bv.point_list, iv.ranges,
                                         iv.tile_order, bv.cub_temp, bv.cub_temp_bytes, st));
     clk_bin.stop();
@@ -727,6 +727,89 @@ int surfel_shard_compact(int P, const int *radii, const float *records, const ui
     return 0;
 }
 
+int surfel_shard_tile_hist(int P, int width, int height, const float *records, const int *radii, uint32_t *hist,
+                           void *stream)
+{
+    if (P < 0 || width <= 0 || height <= 0 || !hist) return fail("surfel_shard_tile_hist", "bad arguments");
+    if (P > 0 && (!records || !radii)) return fail("surfel_shard_tile_hist", "NULL required pointer");
+    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    launch_tile_hist(P, gx, gy, records, radii, hist, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_shard_tile_hist", e);
+}
+
+size_t surfel_shard_partition_bytes(int width, int height)
+{
+    if (width <= 0 || height <= 0) { fail("surfel_shard_partition_bytes", "bad image size"); return 0; }
+    return partition_temp_bytes(((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y));
+}
+
+int surfel_shard_partition(int width, int height, int G, const uint32_t *hist, int cost_base, char *temp, int *cuts,
+                           int64_t *window_num_rendered, void *stream)
+{
+    if (width <= 0 || height <= 0 || G < 1 || G > MAX_RANKS || cost_base < 0)
+        return fail("surfel_shard_partition", "bad sizes (1 <= G <= 16)");
+    if (!hist || !temp || !cuts || !window_num_rendered) return fail("surfel_shard_partition", "NULL required pointer");
+    const int ntiles = ((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
+    launch_partition(ntiles, G, hist, (uint32_t)cost_base, temp, cuts, reinterpret_cast<long long *>(window_num_rendered),
+                     static_cast<cudaStream_t>(stream));
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_shard_partition", e);
+}
+
+size_t surfel_shard_route_bytes(int P, int G)
+{
+    if (P < 0 || G < 1 || G > MAX_RANKS) { fail("surfel_shard_route_bytes", "bad sizes"); return 0; }
+    return route_temp_bytes(P, G);
+}
+
+int surfel_shard_route_count(int P, int width, int height, int G, const float *records, const int *radii,
+                             const int *cuts, char *temp, int *send_counts, void *stream)
+{
+    if (P < 0 || width <= 0 || height <= 0 || G < 1 || G > MAX_RANKS) return fail("surfel_shard_route_count", "bad sizes");
+    if (!cuts || !send_counts || (P > 0 && (!records || !radii || !temp)))
+        return fail("surfel_shard_route_count", "NULL required pointer");
+    const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    const cudaError_t e = run_route_count(P, gx, gy, G, records, radii, cuts, temp, send_counts,
+                                          static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_shard_route_count", e);
+}
+
+int surfel_shard_route_scatter(int P, int G, const float *records, const int *radii, const uint32_t *depth_keys,
+                               char *temp, const int *send_counts, float *send_rows, uint32_t *send_src, void *stream)
+{
+    if (P < 0 || G < 1 || G > MAX_RANKS) return fail("surfel_shard_route_scatter", "bad sizes");
+    if (P == 0) return 0;
+    if (!records || !radii || !depth_keys || !temp || !send_counts) return fail("surfel_shard_route_scatter", "NULL required pointer");
+    if (!aligned(records, 16) || (send_rows && !aligned(send_rows, 16))) return fail("surfel_shard_route_scatter", "alignment");
+    const cudaError_t e = run_route_scatter(P, G, records, radii, depth_keys, temp, send_counts, send_rows, send_src,
+                                            static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_shard_route_scatter", e);
+}
+
+int surfel_window_unpack(int n, const float *rows, float *records, int *radii, uint32_t *depth_keys, void *stream)
+{
+    if (n < 0) return fail("surfel_window_unpack", "bad sizes");
+    if (n == 0) return 0;
+    if (!rows || !records || !radii || !depth_keys) return fail("surfel_window_unpack", "NULL required pointer");
+    if (!aligned(rows, 16) || !aligned(records, 16)) return fail("surfel_window_unpack", "alignment");
+    launch_unpack_rows(n, rows, records, depth_keys, radii, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_window_unpack", e);
+}
+
+int surfel_shard_grad_accumulate(int P, int64_t n_rows, const float *grad_rows, const uint32_t *send_src,
+                                 float *grad_records, void *stream)
+{
+    if (P < 0 || n_rows < 0) return fail("surfel_shard_grad_accumulate", "bad sizes");
+    if (P == 0) return 0;
+    if (!grad_records || (n_rows > 0 && (!grad_rows || !send_src))) return fail("surfel_shard_grad_accumulate", "NULL required pointer");
+    if (!aligned(grad_records, 16) || (grad_rows && !aligned(grad_rows, 16))) return fail("surfel_shard_grad_accumulate", "alignment");
+    const cudaError_t e = run_grad_accumulate(P, (long long)n_rows, grad_rows, send_src, grad_records,
+                                              static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("surfel_shard_grad_accumulate", e);
+}
+
 size_t surfel_window_bytes(int P_total)
 {
     if (P_total < 0) { fail("surfel_window_bytes", "negative P"); return 0; }
@@ -736,37 +819,39 @@ size_t surfel_window_bytes(int P_total)
     return (size_t)(w.cub_temp + cub) + 128;
 }
 
-int surfel_window_prepare(int P_total, int width, int height, int row_offset, int row_stride, const float *records,
+int surfel_window_prepare(int P_total, int width, int height, int tile_lo, int tile_hi, const float *records,
                           const int *radii, const uint32_t *depth_keys, char *window_buffer, int64_t *num_rendered,
                           void *stream, int debug)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!num_rendered) return fail("surfel_window_prepare", "num_rendered is NULL");
-    *num_rendered = 0;
-    if (P_total < 0 || width <= 0 || height <= 0 || row_offset < 0 || row_stride < 1)
+    if (num_rendered) *num_rendered = 0;
+    if (P_total < 0 || width <= 0 || height <= 0 || tile_lo < 0 || tile_hi < tile_lo)
         return fail("surfel_window_prepare", "bad sizes");
     if (P_total == 0) return 0;
     if (!records || !radii || !depth_keys || !window_buffer) return fail("surfel_window_prepare", "NULL required pointer");
     const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
     WindowView w = carve_window(window_buffer, P_total, depth_sort_temp_bytes(P_total));
-    launch_count_window_tiles(P_total, gx, gy, row_offset, row_stride, records, radii, w.tiles_touched, w.idx_in, st);
+    if (tile_hi > gx * gy) return fail("surfel_window_prepare", "tile range exceeds the tile grid");
+    launch_count_window_tiles(P_total, gx, gy, tile_lo, tile_hi, records, radii, w.tiles_touched, w.idx_in, st);
     STAGE("window tile count");
     CK("depth order", run_depth_order(P_total, depth_keys, w.depth_key_sorted, w.idx_in, w.idx_sorted, w.tiles_touched,
                                       w.offsets, nullptr, w.cub_temp, w.cub_temp_bytes, st));
     STAGE("depth order");
-    uint32_t r32 = 0;
-    CK("num_rendered readback", read_back_u32(w.offsets + (P_total - 1), &r32, st));
-    *num_rendered = (int64_t)r32;
+    if (num_rendered) {
+        uint32_t r32 = 0;
+        CK("num_rendered readback", read_back_u32(w.offsets + (P_total - 1), &r32, st));
+        *num_rendered = (int64_t)r32;
+    }
     return 0;
 }
 
-int surfel_window_render(int P_total, int width, int height, int row_offset, int row_stride, int64_t num_rendered,
+int surfel_window_render(int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
                          const float *background, const float *records, const int *radii, char *window_buffer,
                          char *binning_buffer, char *image_buffer, float *out_color, float *out_others, void *stream,
                          int debug)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (P_total < 0 || width <= 0 || height <= 0 || num_rendered < 0 || row_offset < 0 || row_stride < 1)
+    if (P_total < 0 || width <= 0 || height <= 0 || num_rendered < 0 || tile_lo < 0 || tile_hi < tile_lo)
         return fail("surfel_window_render", "bad sizes");
     if (!background || !image_buffer || !out_color || !out_others) return fail("surfel_window_render", "NULL required pointer");
     if (P_total > 0 && (!records || !radii || !window_buffer)) return fail("surfel_window_render", "NULL geometry");
@@ -777,12 +862,13 @@ int surfel_window_render(int P_total, int width, int height, int row_offset, int
     BinView bv{};
     if (P_total > 0) w = carve_window(window_buffer, P_total, depth_sort_temp_bytes(P_total));
     if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
-    CK("tile binning", run_tile_binning(P_total, num_rendered, gx, gy, row_offset, row_stride, records, radii,
+    if (tile_hi > gx * gy) return fail("surfel_window_render", "tile range exceeds the tile grid");
+    CK("tile binning", run_tile_binning(P_total, num_rendered, gx, gy, tile_lo, tile_hi, records, radii,
                                         w.idx_sorted, w.offsets, bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted,
                                         bv.point_list, iv.ranges, iv.tile_order, bv.cub_temp, bv.cub_temp_bytes, st));
     STAGE("tile binning");
     RenderFwdArgs r;
-    r.W = width; r.H = height; r.gx = gx; r.gy = gy; r.row_offset = row_offset; r.row_stride = row_stride;
+    r.W = width; r.H = height; r.gx = gx; r.gy = gy; r.tile_lo = tile_lo; r.tile_hi = tile_hi;
     r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = records; r.bg = background;
     r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
     r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
@@ -791,12 +877,12 @@ int surfel_window_render(int P_total, int width, int height, int row_offset, int
     return 0;
 }
 
-int surfel_window_backward(int P_total, int width, int height, int row_offset, int row_stride, int64_t num_rendered,
+int surfel_window_backward(int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
                            const float *background, const float *records, char *binning_buffer, char *image_buffer,
                            const float *dL_dpix, const float *dL_dothers, float *grad_records, void *stream, int debug)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (P_total < 0 || width <= 0 || height <= 0 || num_rendered < 0 || row_offset < 0 || row_stride < 1)
+    if (P_total < 0 || width <= 0 || height <= 0 || num_rendered < 0 || tile_lo < 0 || tile_hi < tile_lo)
         return fail("surfel_window_backward", "bad sizes");
     if (P_total == 0) return 0;
     if (!background || !records || !image_buffer || !dL_dpix || !dL_dothers || !grad_records)
@@ -809,7 +895,7 @@ int surfel_window_backward(int P_total, int width, int height, int row_offset, i
     ImageView iv = carve_image(image_buffer, width, height);
     BinView bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
     RenderBwdArgs r;
-    r.W = width; r.H = height; r.gx = gx; r.gy = gy; r.row_offset = row_offset; r.row_stride = row_stride;
+    r.W = width; r.H = height; r.gx = gx; r.gy = gy; r.tile_lo = tile_lo; r.tile_hi = tile_hi;
     r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = records; r.bg = background;
     r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
     r.dL_dpix = dL_dpix; r.dL_dothers = dL_dothers; r.gacc = grad_records; r.subtile_cull = g_subtile_cull;

@@ -36,18 +36,19 @@ cudaError_t run_depth_order(int P, const uint32_t *depth_key, uint32_t *depth_ke
     return inclusive_scan_gathered(P, tiles_touched, idx_sorted, offsets, temp, temp_bytes, stream);
 }
 
-// A tile-row window {y : y >= row_offset, (y - row_offset) % row_stride == 0} selects the tile rows a
-// rank renders in the sharded path (row_offset = 0, row_stride = 1: the whole screen).
-__device__ __forceinline__ int first_row_in_window(const int y0, const int row_offset, const int row_stride)
+// A window = the tiles [tile_lo, tile_hi) in row-major order (tile id = y * gx + x) that one call bins and blends.
+// Single GPU: [0, gx * gy).  Sharded path: the contiguous, cost-balanced tile range of this rank (exchange.cu).
+// Row y of a splat's rect [x0, x1) x [y0, y1) contributes its tiles [max(x0, tile_lo - y gx), min(x1, tile_hi - y gx)).
+__device__ __forceinline__ void window_row_span(const int y, const int gx, const int x0, const int x1, const int tile_lo,
+                                                const int tile_hi, int &xs, int &xe)
 {
-    if (y0 <= row_offset) return row_offset;
-    const int k = (y0 - row_offset + row_stride - 1) / row_stride;
-    return row_offset + k * row_stride;
+    xs = max(x0, tile_lo - y * gx);
+    xe = min(x1, tile_hi - y * gx);
 }
 
 // One thread per depth-ordered Gaussian: write its (tile id, Gaussian id) instances.
 __global__ void __launch_bounds__(256)
-emit_instances_kernel(const int P, const int gx, const int gy, const int row_offset, const int row_stride,
+emit_instances_kernel(const int P, const int gx, const int gy, const int tile_lo, const int tile_hi,
                       const float *__restrict__ rec, const int *__restrict__ radii,
                       const uint32_t *__restrict__ idx_sorted, const uint32_t *__restrict__ offsets,
                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
@@ -65,18 +66,21 @@ emit_instances_kernel(const int P, const int gx, const int gy, const int row_off
     const int y0 = min(gy, max(0, (int)((py - r) / TILE_Y)));
     const int x1 = min(gx, max(0, (int)((px + r + TILE_X - 1) / TILE_X)));
     const int y1 = min(gy, max(0, (int)((py + r + TILE_Y - 1) / TILE_Y)));
-    for (int y = first_row_in_window(y0, row_offset, row_stride); y < y1; y += row_stride)
-        for (int x = x0; x < x1; x++) {
+    for (int y = y0; y < y1; y++) {
+        int xs, xe;
+        window_row_span(y, gx, x0, x1, tile_lo, tile_hi, xs, xe);
+        for (int x = xs; x < xe; x++) {
             keys[off] = (uint32_t)(y * gx + x);
             vals[off] = g;
             off++;
         }
+    }
 }
 
 // Tiles of each Gaussian's rect that fall into the window (sharded path; the single-GPU path gets the
 // full count from preprocess).
 __global__ void __launch_bounds__(256)
-count_window_tiles_kernel(const int P, const int gx, const int gy, const int row_offset, const int row_stride,
+count_window_tiles_kernel(const int P, const int gx, const int gy, const int tile_lo, const int tile_hi,
                           const float *__restrict__ rec, const int *__restrict__ radii,
                           uint32_t *__restrict__ tiles_touched, uint32_t *__restrict__ idx_in)
 {
@@ -91,17 +95,20 @@ count_window_tiles_kernel(const int P, const int gx, const int gy, const int row
         const int y0 = min(gy, max(0, (int)((py - r) / TILE_Y)));
         const int x1 = min(gx, max(0, (int)((px + r + TILE_X - 1) / TILE_X)));
         const int y1 = min(gy, max(0, (int)((py + r + TILE_Y - 1) / TILE_Y)));
-        const int yf = first_row_in_window(y0, row_offset, row_stride);
-        if (yf < y1) n = (uint32_t)(((y1 - 1 - yf) / row_stride + 1) * (x1 - x0));
+        for (int y = y0; y < y1; y++) {
+            int xs, xe;
+            window_row_span(y, gx, x0, x1, tile_lo, tile_hi, xs, xe);
+            n += (uint32_t)max(xe - xs, 0);
+        }
     }
     tiles_touched[g] = n;
 }
 
-void launch_count_window_tiles(int P, int gx, int gy, int row_offset, int row_stride, const float *rec,
+void launch_count_window_tiles(int P, int gx, int gy, int tile_lo, int tile_hi, const float *rec,
                                const int *radii, uint32_t *tiles_touched, uint32_t *idx_in, cudaStream_t stream)
 {
     if (P == 0) return;
-    count_window_tiles_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, gy, row_offset, row_stride, rec, radii,
+    count_window_tiles_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, gy, tile_lo, tile_hi, rec, radii,
                                                                    tiles_touched, idx_in);
 }
 
@@ -126,16 +133,13 @@ tile_ranges_kernel(const int64_t R, const uint32_t *__restrict__ keys_sorted, ui
 // Launch order of the tiles of a window: longest instance lists first (buckets of floor(log2(len))),
 // so that the few very long lists start at t = 0 instead of forming the tail of the blend kernels.
 __global__ void __launch_bounds__(1024)
-order_tiles_kernel(const int gx, const int rows, const int row_offset, const int row_stride,
-                   const uint2 *__restrict__ ranges, uint32_t *__restrict__ order)
+order_tiles_kernel(const int tile_lo, const int n, const uint2 *__restrict__ ranges, uint32_t *__restrict__ order)
 {
     __shared__ uint32_t hist[33], base[33];
-    const int n = gx * rows;
     if (threadIdx.x < 33) hist[threadIdx.x] = 0;
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const int tile = (row_offset + row_stride * (j / gx)) * gx + j % gx;
-        const uint2 r = ranges[tile];
+        const uint2 r = ranges[tile_lo + j];
         atomicAdd(&hist[32 - __clz(r.y - r.x)], 1u);
     }
     __syncthreads();
@@ -145,33 +149,32 @@ order_tiles_kernel(const int gx, const int rows, const int row_offset, const int
     }
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const int tile = (row_offset + row_stride * (j / gx)) * gx + j % gx;
-        const uint2 r = ranges[tile];
-        order[atomicAdd(&base[32 - __clz(r.y - r.x)], 1u)] = (uint32_t)tile;
+        const uint2 r = ranges[tile_lo + j];
+        order[atomicAdd(&base[32 - __clz(r.y - r.x)], 1u)] = (uint32_t)(tile_lo + j);
     }
 }
 
-cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, int row_stride, const float *rec,
+cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int tile_lo, int tile_hi, const float *rec,
                              const int *radii,
                              const uint32_t *idx_sorted, const uint32_t *offsets, uint32_t *keys_unsorted,
                              uint32_t *vals_unsorted, uint32_t *keys_sorted, uint32_t *point_list, uint2 *ranges,
                              uint32_t *tile_order, char *temp, size_t temp_bytes, cudaStream_t stream)
 {
     cudaError_t e = cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream);
-    const int rows = gy > row_offset ? (gy - row_offset + row_stride - 1) / row_stride : 0;
+    const int ntiles = tile_hi > tile_lo ? tile_hi - tile_lo : 0;
     if (e != cudaSuccess) return e;
     if (R == 0 || P == 0) {
-        if (rows > 0) order_tiles_kernel<<<1, 1024, 0, stream>>>(gx, rows, row_offset, row_stride, ranges, tile_order);
+        if (ntiles > 0) order_tiles_kernel<<<1, 1024, 0, stream>>>(tile_lo, ntiles, ranges, tile_order);
         return cudaGetLastError();
     }
-    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, gy, row_offset, row_stride, rec, radii,
+    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, gy, tile_lo, tile_hi, rec, radii,
                                                                idx_sorted, offsets, keys_unsorted, vals_unsorted);
     int bits = 1;
     while ((1u << bits) < (uint32_t)(gx * gy)) bits++;
     e = radix_sort_pairs(keys_unsorted, vals_unsorted, keys_sorted, point_list, R, bits, temp, temp_bytes, stream);
     if (e != cudaSuccess) return e;
     tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, keys_sorted, ranges);
-    if (rows > 0) order_tiles_kernel<<<1, 1024, 0, stream>>>(gx, rows, row_offset, row_stride, ranges, tile_order);
+    if (ntiles > 0) order_tiles_kernel<<<1, 1024, 0, stream>>>(tile_lo, ntiles, ranges, tile_order);
     return cudaGetLastError();
 }
 

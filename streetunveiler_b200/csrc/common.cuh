@@ -44,6 +44,11 @@ constexpr int REC_BYTES = REC_FLOATS * 4;
 //   [15..17] dL_dnormal, [18..19] pad
 constexpr int GACC_FLOATS = 20;
 
+// Multi-GPU exchange (exchange.cu): a projected record travels as a 112-B row = record (24 floats) + depth key bits +
+// radius (int bits) + 2 pad words; at most MAX_RANKS ranks share one scene.
+constexpr int XROW_FLOATS = 28;
+constexpr int MAX_RANKS = 16;
+
 // Class-probability pass (render_fwd.cu / render_bwd.cu, CLASSES = true): channels rendered in one traversal.
 constexpr int MAX_CLASSES = 8;
 

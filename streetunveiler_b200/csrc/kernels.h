@@ -54,6 +54,20 @@ cudaError_t run_compact_visible(int P, const int *radii, const float *rec, const
                                 int *radii_c, uint32_t *keys_c, uint32_t *slot, int *count_dev, char *temp,
                                 size_t temp_bytes, cudaStream_t stream);
 
+// ---- multi-GPU exchange (exchange.cu) ----
+void launch_tile_hist(int P, int gx, int gy, const float *rec, const int *radii, uint32_t *hist, cudaStream_t stream);
+size_t partition_temp_bytes(int ntiles);
+void launch_partition(int ntiles, int G, const uint32_t *hist, uint32_t cost_base, char *temp, int *cuts,
+                      long long *window_R, cudaStream_t stream);
+size_t route_temp_bytes(int P, int G);
+cudaError_t run_route_count(int P, int gx, int gy, int G, const float *rec, const int *radii, const int *cuts,
+                            char *temp, int *send_counts, cudaStream_t stream);
+cudaError_t run_route_scatter(int P, int G, const float *rec, const int *radii, const uint32_t *keys, char *temp,
+                              const int *send_counts, float *send_rows, uint32_t *send_src, cudaStream_t stream);
+void launch_unpack_rows(int n, const float *rows, float *rec, uint32_t *keys, int *radii, cudaStream_t stream);
+cudaError_t run_grad_accumulate(int P, long long n_rows, const float *rows, const uint32_t *src, float *gacc,
+                                cudaStream_t stream);
+
 // ---- binning (binning.cu) ----
 size_t depth_sort_temp_bytes(int P);
 size_t tile_sort_temp_bytes(int64_t R);
@@ -62,9 +76,9 @@ cudaError_t run_depth_order(int P, const uint32_t *depth_key, uint32_t *depth_ke
                             uint32_t *idx_sorted, const uint32_t *tiles_touched, uint32_t *offsets,
                             int64_t *num_rendered_dev, char *temp, size_t temp_bytes, cudaStream_t stream);
 // emit (tile, id) pairs in depth order, stable-sort by tile, find per-tile ranges
-void launch_count_window_tiles(int P, int gx, int gy, int row_offset, int row_stride, const float *rec,
+void launch_count_window_tiles(int P, int gx, int gy, int tile_lo, int tile_hi, const float *rec,
                                const int *radii, uint32_t *tiles_touched, uint32_t *idx_in, cudaStream_t stream);
-cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, int row_stride, const float *rec,
+cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int tile_lo, int tile_hi, const float *rec,
                              const int *radii,
                              const uint32_t *idx_sorted, const uint32_t *offsets, uint32_t *keys_unsorted,
                              uint32_t *vals_unsorted, uint32_t *keys_sorted, uint32_t *point_list, uint2 *ranges,
@@ -73,9 +87,9 @@ cudaError_t run_tile_binning(int P, int64_t R, int gx, int gy, int row_offset, i
 // ---- render (render_fwd.cu / render_bwd.cu) ----
 struct RenderFwdArgs {
     int W, H, gx, gy;
-    int row_offset = 0, row_stride = 1;  // tile-row window rendered by this call
+    int tile_lo = 0, tile_hi = -1;       // window [tile_lo, tile_hi) of row-major tile ids rendered by this call (-1: all)
     const uint2 *ranges;
-    const uint32_t *tile_order;  // launch order of the window's tiles (longest lists first)
+    const uint32_t *tile_order;  // launch order of the window's tiles (longest lists first); entries are tile ids
     const uint32_t *point_list;
     const float *rec;
     const float *bg;
@@ -90,7 +104,7 @@ void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream);
 
 struct RenderBwdArgs {
     int W, H, gx, gy;
-    int row_offset = 0, row_stride = 1;
+    int tile_lo = 0, tile_hi = -1;
     const uint2 *ranges;
     const uint32_t *tile_order;
     const uint32_t *point_list;

@@ -130,7 +130,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    // blockIdx.x enumerates the tiles of this call's row window, longest instance lists first
+    // blockIdx.x enumerates the tiles of this call's window, longest instance lists first
     const int tile = (int)tile_order[blockIdx.x];
     const uint2 range = ranges[tile];
     // only list positions [0, total) can have been blended by some pixel of this tile
@@ -388,9 +388,8 @@ static void launch_one(const RenderBwdArgs &a, const int tiles, const int *flag,
 
 void launch_render_bwd(const RenderBwdArgs &a, cudaStream_t stream)
 {
-    const int rows = a.gy > a.row_offset ? (a.gy - a.row_offset + a.row_stride - 1) / a.row_stride : 0;
-    const int tiles = a.gx * rows;
-    if (tiles == 0) return;
+    const int tiles = (a.tile_hi < 0 ? a.gx * a.gy : a.tile_hi) - a.tile_lo;
+    if (tiles <= 0) return;
     if (a.n_classes > 0) {   // class-probability pass: no aux outputs exist
         launch_one<true, false, 72, true>(a, tiles, nullptr, stream);
         return;

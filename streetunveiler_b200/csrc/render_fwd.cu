@@ -43,7 +43,7 @@ render_fwd_kernel(const int n_classes,
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    // blockIdx.x enumerates the tiles of this call's row window, longest instance lists first
+    // blockIdx.x enumerates the tiles of this call's window, longest instance lists first
     const int tile = (int)tile_order[blockIdx.x];
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
@@ -219,9 +219,8 @@ static void launch_fwd(const RenderFwdArgs &a, const int tiles, cudaStream_t str
 
 void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream)
 {
-    const int rows = a.gy > a.row_offset ? (a.gy - a.row_offset + a.row_stride - 1) / a.row_stride : 0;
-    const int tiles = a.gx * rows;
-    if (tiles == 0) return;
+    const int tiles = (a.tile_hi < 0 ? a.gx * a.gy : a.tile_hi) - a.tile_lo;
+    if (tiles <= 0) return;
     if (a.n_classes > 0)
         launch_fwd<true, true>(a, tiles, stream);
     else if (a.subtile_cull)

@@ -2,25 +2,36 @@
 
 Why not "every rank blends its own Gaussians and the images are summed": front-to-back alpha blending
 is an ordered product, so a sum of per-shard images is not the reference image.  The
-exact scheme used here keeps parameters, gradients and optimiser state sharded by Gaussian index and
-exchanges only *projected* data:
+exact scheme used here keeps parameters, gradients and optimiser state sharded by Gaussian index,
+partitions the SCREEN, and exchanges only *projected* data -- and only with the ranks that need it:
 
-  forward   1. every rank projects its own shard            (surfel_shard_preprocess, 96-B records) and keeps
-               the rows that survived culling, in index order (surfel_shard_compact) -- typically a
-               fifth of a street scene is in view, so the exchanges below shrink by that factor
-            2. all-gather of the compact records / radii / depth keys, padded to the largest count
-               (NCCL over NVLink; one tiny all-gather of the counts first)
-            3. every rank bins + blends ALL Gaussians for its own tile rows (rows r, r+G, r+2G, ...;
-               interleaved for load balance)               (surfel_window_prepare / _render)
-            4. all-reduce(sum) of the ten image planes      (each rank wrote only its rows, the rest is 0)
-  backward  5. every rank back-propagates its tile rows into 80-B gradient records of ALL Gaussians
-                                                           (surfel_window_backward)
-            6. reduce-scatter(sum) of the gradient records to the owners of the Gaussians
-            7. every rank turns its records into parameter gradients (surfel_shard_backward; Gaussian i
-               reads compact row slot[i])
+  forward   1. every rank projects its own shard                        (surfel_shard_preprocess, 96-B records)
+            2. per-tile instance histogram of the shard, all-reduce(sum) -> the frame's global histogram;
+               every rank cuts the row-major tile order into G contiguous ranges of equal cost
+               (surfel_shard_tile_hist / surfel_shard_partition; cost = instances + a constant per tile).
+               The same kernel yields every range's exact instance count, so no num_rendered read-back
+               follows later.
+            3. per-destination send counts (a record goes to every rank whose range its tile rect touches:
+               1.1-1.3 ranks on average instead of all G), all-gather of the G x G count matrix -- the ONE
+               host synchronisation of the forward (sizes of the exchange buffers)
+            4. stable per-destination scatter into 112-B rows (record + depth key + radius), all-to-all
+               over NCCL/NVLink.  Segments arrive in rank order and keep index order inside, i.e. global
+               index order, so the receiver's stable depth sort breaks ties exactly like one GPU does.
+            5. every rank depth-sorts, bins and blends what it received for its own tiles
+               (surfel_window_unpack / _prepare / _render): same lists, order and arithmetic per pixel as
+               on one GPU
+            6. all-reduce(sum) of the ten image planes (each pixel has exactly one non-zero summand, so
+               the sum is exact)
+  backward  7. every rank back-propagates its tiles into 80-B gradient rows of the records it received
+                                                                     (surfel_window_backward)
+            8. all-to-all of the gradient rows back along the same routes; the owner sums the rows of a
+               Gaussian that went to several ranks (surfel_shard_grad_accumulate)
+            9. every rank turns its accumulator into parameter gradients (surfel_shard_backward)
 
-Every pixel sees exactly the list, order and arithmetic of the single-GPU path, so the forward is
-bit-identical to it and gradients differ only by float-add order.
+Contract: the upstream gradients (dL/dcolor, dL/dallmap) must be THE SAME on every rank -- each rank
+back-propagates only its own tiles and trusts its local copy for them (a loss computed identically on
+the all-reduced image satisfies this).  ``ShardedRasterizer(check_replicated=True)`` verifies it with
+one all-reduce of a checksum per backward.
 
 The compute stages sit behind a small backend object so that the collective choreography can be
 tested on CPU (gloo, world_size 2) with a toy backend (tests/test_sharded_gloo.py).
@@ -35,13 +46,16 @@ import torch.distributed as dist
 
 REC_FLOATS = 24
 GREC_FLOATS = 20
-ROW_QUANTUM = 4096   # exchanged row counts are rounded up to this (stable buffer shapes from step to step)
+XROW_FLOATS = 28     # exchanged row: record + depth key + radius + 2 pad words (csrc/common.cuh)
+TILE = 16
+COST_BASE = 16       # per-tile constant of the partition's cost model, in units of one tile instance
 
 # SURFEL_SHARD_TIMING=1: synchronise around every phase and record wall-clock per phase and call (diagnostics only)
 import os as _os
 import time as _time
 _TIMING = _os.environ.get("SURFEL_SHARD_TIMING") == "1"
 PHASE_MS = {}
+LAST_INFO = {}       # diagnostics of the most recent forward on this rank (cuts, counts, routed rows)
 
 
 class _phase:
@@ -60,7 +74,7 @@ class _phase:
 
 
 # ----------------------------------------------------------------------------------------------------
-# collectives with gloo fallbacks (gloo has no reduce_scatter; used only by the CPU tests)
+# collectives (gloo is used only by the CPU tests)
 # ----------------------------------------------------------------------------------------------------
 def _all_gather_rows(x: torch.Tensor, group) -> torch.Tensor:
     world = dist.get_world_size(group)
@@ -74,20 +88,16 @@ def _all_gather_rows(x: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
-def _reduce_scatter_rows(x: torch.Tensor, group) -> torch.Tensor:
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    n = x.shape[0] // world
-    out = x.new_empty((n,) + tuple(x.shape[1:]))
-    if dist.get_backend(group) == "gloo":
-        y = x.clone()
-        dist.all_reduce(y, group=group)
-        return y[rank * n:(rank + 1) * n].contiguous()
-    dist.reduce_scatter_tensor(out, x.contiguous(), group=group)
+def _all_to_all_rows(x: torch.Tensor, in_splits, out_splits, group) -> torch.Tensor:
+    """Rows [sum(in_splits), ...] split by destination -> rows [sum(out_splits), ...] concatenated by source."""
+    out = x.new_empty((int(sum(out_splits)),) + tuple(x.shape[1:]))
+    dist.all_to_all_single(out, x.contiguous(), output_split_sizes=list(out_splits), input_split_sizes=list(in_splits),
+                           group=group)
     return out
 
 
 def pad_rows(x: torch.Tensor, n: int, value=0) -> torch.Tensor:
-    """Pad the first dimension to n rows (shards may differ in size; collectives need equal shapes)."""
+    """Pad the first dimension to n rows."""
     if x.shape[0] == n:
         return x.contiguous()
     pad = x.new_full((n - x.shape[0],) + tuple(x.shape[1:]), value)
@@ -127,7 +137,8 @@ class NativeBackend:
         return radii, rec, keys, clamped
 
     def shard_compact(self, radii, rec, keys):
-        """-> (rec_c, radii_c, keys_c [P rows of capacity each], slot [P], count [1] int32 on the device)."""
+        """Round-1 exchange helper, kept for callers of the all-gather scheme.
+        -> (rec_c, radii_c, keys_c [P rows of capacity each], slot [P], count [1] int32 on the device)."""
         P, dev = radii.shape[0], radii.device
         rec_c = torch.empty_like(rec)
         radii_c = torch.empty_like(radii)
@@ -142,35 +153,91 @@ class NativeBackend:
                         "surfel_shard_compact")
         return rec_c, radii_c, keys_c, slot, count
 
-    def window_forward(self, s, rec_all, radii_all, keys_all, row_offset, row_stride):
-        L, p, dev = self.L, self._p, rec_all.device
-        Pt, W, H = rec_all.shape[0], s.image_width, s.image_height
-        u8 = dict(dtype=torch.uint8, device=dev)
-        win = torch.empty((self._lib.size(L.surfel_window_bytes(Pt), "surfel_window_bytes"),), **u8)
-        img = torch.empty((self._lib.size(L.surfel_image_bytes(W, H), "surfel_image_bytes"),), **u8)
-        R = C.c_int64(0)
-        st = self._stream()
-        self._lib.check(L.surfel_window_prepare(Pt, W, H, row_offset, row_stride, p(rec_all), p(radii_all), p(keys_all),
-                                                p(win), C.byref(R), st, int(bool(s.debug))), "surfel_window_prepare")
-        R = int(R.value)
-        binb = torch.empty((self._lib.size(L.surfel_binning_bytes(R), "surfel_binning_bytes") if R else 0,), **u8)
-        color = torch.zeros((3, H, W), dtype=torch.float32, device=dev)   # rows of other ranks stay 0 for the all-reduce
-        others = torch.zeros((7, H, W), dtype=torch.float32, device=dev)
-        self._lib.check(L.surfel_window_render(Pt, W, H, row_offset, row_stride, R, p(s.bg), p(rec_all), p(radii_all),
-                                               p(win), p(binb), p(img), p(color), p(others), st, int(bool(s.debug))),
-                        "surfel_window_render")
-        return color, others, (R, binb, img, row_offset, row_stride)
+    def tile_hist(self, s, rec, radii):
+        W, H, dev = s.image_width, s.image_height, rec.device
+        tiles = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
+        hist = torch.empty((tiles,), dtype=torch.int32, device=dev)
+        self._lib.check(self.L.surfel_shard_tile_hist(rec.shape[0], W, H, self._p(rec), self._p(radii),
+                                                      C.c_void_p(hist.data_ptr()), self._stream()), "surfel_shard_tile_hist")
+        return hist
 
-    def window_backward(self, s, rec_all, state, dL_dcolor, dL_dothers):
-        R, binb, img, row_offset, row_stride = state
-        Pt = rec_all.shape[0]
-        grec = torch.empty((Pt, GREC_FLOATS), dtype=torch.float32, device=rec_all.device)
+    def partition(self, s, hist, world):
+        """-> one int64 device tensor [G + 1 + G]: cuts (tile ids) followed by every range's instance count."""
+        W, H, dev = s.image_width, s.image_height, hist.device
+        tmp = torch.empty((self._lib.size(self.L.surfel_shard_partition_bytes(W, H), "surfel_shard_partition_bytes"),),
+                          dtype=torch.uint8, device=dev)
+        cuts = torch.empty((world + 1,), dtype=torch.int32, device=dev)
+        wr = torch.empty((world,), dtype=torch.int64, device=dev)
+        self._lib.check(self.L.surfel_shard_partition(W, H, world, C.c_void_p(hist.data_ptr()), COST_BASE,
+                                                      C.c_void_p(tmp.data_ptr()), C.c_void_p(cuts.data_ptr()),
+                                                      C.c_void_p(wr.data_ptr()), self._stream()), "surfel_shard_partition")
+        return cuts, wr
+
+    def route_count(self, s, rec, radii, cuts, world):
+        P, dev = rec.shape[0], rec.device
+        tmp = torch.empty((self._lib.size(self.L.surfel_shard_route_bytes(P, world), "surfel_shard_route_bytes"),),
+                          dtype=torch.uint8, device=dev)
+        counts = torch.empty((world,), dtype=torch.int32, device=dev)
+        self._lib.check(self.L.surfel_shard_route_count(P, s.image_width, s.image_height, world, self._p(rec),
+                                                        self._p(radii), C.c_void_p(cuts.data_ptr()),
+                                                        C.c_void_p(tmp.data_ptr()), C.c_void_p(counts.data_ptr()),
+                                                        self._stream()), "surfel_shard_route_count")
+        return tmp, counts
+
+    def route_scatter(self, rec, radii, keys, route_state, send_counts_dev, n_send, world):
+        dev = rec.device
+        rows = torch.empty((n_send, XROW_FLOATS), dtype=torch.float32, device=dev)
+        src = torch.empty((n_send,), dtype=torch.int32, device=dev)
+        self._lib.check(self.L.surfel_shard_route_scatter(rec.shape[0], world, self._p(rec), self._p(radii), self._p(keys),
+                                                          C.c_void_p(route_state.data_ptr()),
+                                                          C.c_void_p(send_counts_dev.data_ptr()), self._p(rows),
+                                                          self._p(src), self._stream()), "surfel_shard_route_scatter")
+        return rows, src
+
+    def unpack(self, rows):
+        n, dev = rows.shape[0], rows.device
+        rec = torch.empty((n, REC_FLOATS), dtype=torch.float32, device=dev)
+        radii = torch.empty((n,), dtype=torch.int32, device=dev)
+        keys = torch.empty((n,), dtype=torch.int32, device=dev)
+        self._lib.check(self.L.surfel_window_unpack(n, self._p(rows), self._p(rec), self._p(radii), self._p(keys),
+                                                    self._stream()), "surfel_window_unpack")
+        return rec, radii, keys
+
+    def window_forward(self, s, rec_w, radii_w, keys_w, tile_lo, tile_hi, R):
+        """Blend the received Gaussians for the tiles [tile_lo, tile_hi); R = the window's instance count (known from
+        the partition).  Planes of other ranks' tiles stay 0 for the all-reduce."""
+        L, p, dev = self.L, self._p, rec_w.device
+        n, W, H = rec_w.shape[0], s.image_width, s.image_height
+        u8 = dict(dtype=torch.uint8, device=dev)
+        win = torch.empty((self._lib.size(L.surfel_window_bytes(n), "surfel_window_bytes"),), **u8)
+        img = torch.empty((self._lib.size(L.surfel_image_bytes(W, H), "surfel_image_bytes"),), **u8)
+        st = self._stream()
+        self._lib.check(L.surfel_window_prepare(n, W, H, tile_lo, tile_hi, p(rec_w), p(radii_w), p(keys_w), p(win), None,
+                                                st, int(bool(s.debug))), "surfel_window_prepare")
+        binb = torch.empty((self._lib.size(L.surfel_binning_bytes(R), "surfel_binning_bytes") if R else 0,), **u8)
+        planes = torch.zeros((10, H, W), dtype=torch.float32, device=dev)
+        color, others = planes[:3], planes[3:]
+        self._lib.check(L.surfel_window_render(n, W, H, tile_lo, tile_hi, R, p(s.bg), p(rec_w), p(radii_w), p(win), p(binb),
+                                               p(img), p(color), p(others), st, int(bool(s.debug))), "surfel_window_render")
+        return planes, (R, binb, img, tile_lo, tile_hi)
+
+    def window_backward(self, s, rec_w, state, dL_dcolor, dL_dothers):
+        R, binb, img, tile_lo, tile_hi = state
+        n = rec_w.shape[0]
+        grows = torch.empty((n, GREC_FLOATS), dtype=torch.float32, device=dL_dcolor.device)
         p = self._p
-        self._lib.check(self.L.surfel_window_backward(
-            Pt, s.image_width, s.image_height, row_offset, row_stride, R, p(s.bg), p(rec_all), p(binb), p(img),
-            p(dL_dcolor.contiguous()), p(dL_dothers.contiguous()), p(grec), self._stream(), int(bool(s.debug))),
-            "surfel_window_backward")
-        return grec
+        if n:
+            self._lib.check(self.L.surfel_window_backward(
+                n, s.image_width, s.image_height, tile_lo, tile_hi, R, p(s.bg), p(rec_w), p(binb), p(img),
+                p(dL_dcolor.contiguous()), p(dL_dothers.contiguous()), p(grows), self._stream(), int(bool(s.debug))),
+                "surfel_window_backward")
+        return grows
+
+    def grad_accumulate(self, P, rows, send_src):
+        gacc = torch.empty((P, GREC_FLOATS), dtype=torch.float32, device=rows.device)
+        self._lib.check(self.L.surfel_shard_grad_accumulate(P, rows.shape[0], self._p(rows), self._p(send_src),
+                                                            self._p(gacc), self._stream()), "surfel_shard_grad_accumulate")
+        return gacc
 
     def shard_backward(self, s, means3D, shs, scales, rotations, radii, rec, clamped, grec, slot):
         P, dev, M = means3D.shape[0], means3D.device, shs.shape[1]
@@ -191,44 +258,67 @@ class NativeBackend:
 # ----------------------------------------------------------------------------------------------------
 class _ShardedRasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, shs, opacities, scales, rotations, settings, backend, group):
+    def forward(ctx, means3D, means2D, shs, opacities, scales, rotations, settings, backend, group, check_replicated):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+        P = means3D.shape[0]
         with _phase("fwd preprocess"):
             radii, rec, keys, clamped = backend.shard_preprocess(settings, means3D.contiguous(), shs.contiguous(),
                                                                  opacities.contiguous(), scales.contiguous(),
                                                                  rotations.contiguous())
-            rec_c, radii_c, keys_c, slot, count = backend.shard_compact(radii, rec, keys)
-        # rows past a rank's count are culled Gaussians: radius 0, depth key 0xFFFFFFFF (sort last, emit nothing)
-        with _phase("fwd counts"):
-            counts = _all_gather_rows(count, group)
-            c_max = -(-max(int(counts.max().item()), 1) // ROW_QUANTUM) * ROW_QUANTUM   # the one host sync of the exchange
-        with _phase("fwd all-gather"):
-            keep = min(c_max, rec_c.shape[0])
-            rec_all = _all_gather_rows(pad_rows(rec_c[:keep], c_max), group)
-            radii_all = _all_gather_rows(pad_rows(radii_c[:keep], c_max), group)
-            keys_all = _all_gather_rows(pad_rows(keys_c[:keep], c_max, -1), group)
+        with _phase("fwd partition (hist all-reduce, cuts)"):
+            hist = backend.tile_hist(settings, rec, radii)
+            dist.all_reduce(hist, group=group)
+            cuts, window_R = backend.partition(settings, hist, world)
+        with _phase("fwd route counts + host sync"):
+            route_state, send_counts = backend.route_count(settings, rec, radii, cuts, world)
+            counts_all = _all_gather_rows(send_counts, group)                      # [G * G]: row s = what rank s sends
+            host = torch.cat([counts_all.to(torch.int64), cuts.to(torch.int64), window_R.to(torch.int64)]).cpu()
+            cmat = host[:world * world].view(world, world)
+            cuts_h = host[world * world:world * world + world + 1].tolist()
+            R = int(host[world * world + world + 1 + rank])
+            in_splits = cmat[rank].tolist()
+            out_splits = cmat[:, rank].tolist()
+        with _phase("fwd scatter + all-to-all"):
+            send_rows, send_src = backend.route_scatter(rec, radii, keys, route_state, send_counts, int(sum(in_splits)),
+                                                        world)
+            recv_rows = _all_to_all_rows(send_rows, in_splits, out_splits, group)
+            del send_rows
         with _phase("fwd window (sort+bin+blend)"):
-            color, others, state = backend.window_forward(settings, rec_all, radii_all, keys_all, rank, world)
+            rec_w, radii_w, keys_w = backend.unpack(recv_rows)
+            del recv_rows
+            planes, state = backend.window_forward(settings, rec_w, radii_w, keys_w, int(cuts_h[rank]),
+                                                   int(cuts_h[rank + 1]), R)
         with _phase("fwd image all-reduce"):
-            planes = torch.cat([color, others], 0)
-            dist.all_reduce(planes, group=group)               # every rank wrote only its tile rows
+            dist.all_reduce(planes, group=group)               # every rank wrote only its tiles
+        LAST_INFO.update(cuts=cuts_h, send=in_splits, recv=out_splits, num_rendered=R, shard=P)
         ctx.settings, ctx.backend, ctx.group, ctx.state = settings, backend, group, state
-        ctx.num_rendered = state[0] if isinstance(state, tuple) else None
-        ctx.save_for_backward(means3D, shs, scales, rotations, radii, rec, clamped, rec_all, slot)
+        ctx.splits = (in_splits, out_splits)
+        ctx.check_replicated = check_replicated
+        ctx.num_rendered = R
+        ctx.save_for_backward(means3D, shs, scales, rotations, radii, rec, clamped, rec_w, send_src)
         ctx.mark_non_differentiable(radii)
-        return planes[:3].contiguous(), radii, planes[3:].contiguous()
+        return planes[:3], radii, planes[3:]
 
     @staticmethod
     def backward(ctx, g_color, g_radii, g_others):
-        means3D, shs, scales, rotations, radii, rec, clamped, rec_all, slot = ctx.saved_tensors
+        means3D, shs, scales, rotations, radii, rec, clamped, rec_w, send_src = ctx.saved_tensors
         s, backend, group = ctx.settings, ctx.backend, ctx.group
+        in_splits, out_splits = ctx.splits
+        if ctx.check_replicated:
+            chk = torch.stack([g_color.double().sum(), g_others.nan_to_num(0.0).double().sum()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            if not torch.equal(lo, hi):
+                raise RuntimeError("ShardedRasterizer: upstream gradients differ between ranks (replicated-loss contract)")
         with _phase("bwd window blend"):
-            grec_all = backend.window_backward(s, rec_all, ctx.state, g_color.contiguous(), g_others.contiguous())
-        with _phase("bwd reduce-scatter"):
-            grec = _reduce_scatter_rows(grec_all, group)
+            grows = backend.window_backward(s, rec_w, ctx.state, g_color.contiguous(), g_others.contiguous())
+        with _phase("bwd all-to-all"):
+            back = _all_to_all_rows(grows, out_splits, in_splits, group)
         with _phase("bwd per-Gaussian"):
-            g = backend.shard_backward(s, means3D, shs, scales, rotations, radii, rec, clamped, grec, slot)
-        return g["means3D"], g["means2D"], g["shs"], g["opacities"], g["scales"], g["rotations"], None, None, None
+            gacc = backend.grad_accumulate(means3D.shape[0], back, send_src)
+            g = backend.shard_backward(s, means3D, shs, scales, rotations, radii, rec, clamped, gacc, None)
+        return g["means3D"], g["means2D"], g["shs"], g["opacities"], g["scales"], g["rotations"], None, None, None, None
 
 
 class ShardedRasterizer:
@@ -236,14 +326,20 @@ class ShardedRasterizer:
 
     ``rasterizer(means3D, means2D, opacities, shs, scales, rotations, settings) -> (color, radii, allmap)``
     where color / allmap are the full images (identical on every rank) and radii belongs to the shard.
+    The upstream gradients given to ``backward`` must be identical on every rank (module docstring);
+    ``check_replicated=True`` verifies that on every backward.
     """
 
-    def __init__(self, world: Optional[int] = None, rank: Optional[int] = None, backend=None, group=None):
+    def __init__(self, world: Optional[int] = None, rank: Optional[int] = None, backend=None, group=None,
+                 check_replicated: bool = False):
         self.group = group
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
+        if self.world > 16:
+            raise ValueError("at most 16 ranks per scene (csrc/common.cuh MAX_RANKS)")
         self.backend = backend if backend is not None else NativeBackend()
+        self.check_replicated = check_replicated
 
     def __call__(self, means3D, means2D, opacities, shs, scales, rotations, settings):
         return _ShardedRasterize.apply(means3D, means2D, shs, opacities, scales, rotations, settings, self.backend,
-                                       self.group)
+                                       self.group, self.check_replicated)

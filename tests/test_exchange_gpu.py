@@ -1,0 +1,132 @@
+"""GPU tests of the multi-GPU exchange kernels (csrc/exchange.cu) on ONE device.
+
+G "virtual ranks" share the GPU: every CUDA stage of streetunveiler_b200/sharded.py runs per rank through the C ABI
+(NativeBackend), and the collectives (all-reduce of the tile histogram, all-gather of the counts, the two all-to-alls,
+the image all-reduce) are replaced by the tensor operations they are defined as.  The result must equal the
+single-GPU operator: forward bit-identical, gradients within 1e-4 -- for 2, 3 and 8 ranks, uneven shards, an empty
+shard.  The torch.distributed side of the same choreography is covered by tests/test_sharded_gloo.py (CPU) and
+tests/multigpu_check.py (real ranks)."""
+import numpy as np
+import pytest
+import torch
+
+import harness as hz
+from streetunveiler_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _virtual_sharded(scene, cam, bounds, grads, bg):
+    from streetunveiler_b200.sharded import NativeBackend
+    be = NativeBackend()
+    dev = torch.device("cuda")
+    G = len(bounds) - 1
+    s = hz._settings(hz.ours_module(), cam, bg, int(scene["sh_degree"]), 1.0, dev)
+    sh = [{k: v[bounds[r]:bounds[r + 1]].to(dev).contiguous() for k, v in scene.items() if isinstance(v, torch.Tensor)}
+          for r in range(G)]
+    pre = [be.shard_preprocess(s, p["means3D"], p["shs"], p["opacities"], p["scales"], p["rotations"]) for p in sh]
+    hist = sum(be.tile_hist(s, rec, radii).to(torch.int64) for radii, rec, keys, clamped in pre).to(torch.int32)
+    cuts, window_R = be.partition(s, hist, G)
+    cuts_h, wr_h = cuts.cpu().tolist(), window_R.cpu().tolist()
+    routes = [be.route_count(s, rec, radii, cuts, G) for radii, rec, keys, clamped in pre]
+    cmat = torch.stack([c for _, c in routes]).cpu()                         # [src, dst]
+    sends = [be.route_scatter(rec, radii, keys, routes[r][0], routes[r][1], int(cmat[r].sum()), G)
+             for r, (radii, rec, keys, clamped) in enumerate(pre)]
+
+    def seg(r, d):   # rows of rank r's send buffer bound for rank d
+        a = int(cmat[r, :d].sum())
+        return slice(a, a + int(cmat[r, d]))
+
+    planes, states, recs_w = torch.zeros(10, cam.height, cam.width, device=dev), [], []
+    for d in range(G):
+        rows = torch.cat([sends[r][0][seg(r, d)] for r in range(G)], 0)      # all-to-all: segments in source-rank order
+        rec_w, radii_w, keys_w = be.unpack(rows)
+        pl, st = be.window_forward(s, rec_w, radii_w, keys_w, cuts_h[d], cuts_h[d + 1], int(wr_h[d]))
+        planes += pl                                                          # image all-reduce
+        states.append(st)
+        recs_w.append(rec_w)
+    gc, ga = grads[0].to(dev), grads[1].to(dev)
+    grows = [be.window_backward(s, recs_w[d], states[d], gc, ga) for d in range(G)]
+    out = {"color": planes[:3].cpu().numpy(), "allmap": planes[3:].cpu().numpy(), "cuts": cuts_h, "window_R": wr_h,
+           "cmat": cmat, "radii": torch.cat([p[0] for p in pre]).cpu().numpy()}
+    g_all = {}
+    for r, (radii, rec, keys, clamped) in enumerate(pre):
+        def rseg(d):   # rows of rank d's receive buffer that came from rank r
+            a = int(cmat[:r, d].sum())
+            return slice(a, a + int(cmat[r, d]))
+        back = torch.cat([grows[d][rseg(d)] for d in range(G)], 0)            # all-to-all back
+        gacc = be.grad_accumulate(rec.shape[0], back, sends[r][1])
+        p = sh[r]
+        g = be.shard_backward(s, p["means3D"], p["shs"], p["scales"], p["rotations"], radii, rec, clamped, gacc, None)
+        for k, v in g.items():
+            g_all.setdefault(k, []).append(v)
+    for k, v in g_all.items():
+        out["g_" + k] = torch.cat(v, 0).cpu().numpy()
+    return out
+
+
+@pytest.mark.parametrize("G,P,mode", [(2, 120_000, "all"), (3, 120_000, "color_alpha"), (8, 400_000, "all")])
+def test_virtual_ranks_equal_single_gpu(G, P, mode):
+    cam = syn.make_camera(960, 640, 1027.5, 1027.5)
+    scene = syn.street_scene(P, 4, 3)
+    grads = syn.upstream_grads(cam.width, cam.height, mode, seed=11)
+    bg = torch.tensor([0.1, 0.3, 0.2])
+    # uneven shards, and (G = 3) an empty one
+    bounds = [0] + [int(P * (r + 1) / G) - (7 * (r + 1) if r + 1 < G else 0) for r in range(G)]
+    if G == 3:
+        bounds[2] = bounds[1]
+    v = _virtual_sharded(scene, cam, bounds, grads, bg)
+    ref = hz.run_ours(scene, cam, bg=bg, grads=grads)
+    # the image all-reduce adds each rank's planes to zeros: exact; the background term T * bg is part of every tile
+    assert np.array_equal(v["color"], ref["color"]) and np.array_equal(v["allmap"], ref["allmap"])
+    assert np.array_equal(v["radii"], ref["radii"])
+    assert sum(v["window_R"]) == ref["num_rendered"]
+    assert v["cuts"][0] == 0 and v["cuts"][-1] == 60 * 40 and all(a <= b for a, b in zip(v["cuts"], v["cuts"][1:]))
+    # cost balance: no range holds more than 1.6x its share of the instances (+ the constant per tile)
+    cost = [r + 16 * (b - a) for r, a, b in zip(v["window_R"], v["cuts"], v["cuts"][1:])]
+    assert max(cost) <= 1.6 * sum(cost) / G, (cost, v["cuts"])
+    # a record goes to few ranks: the exchange moves less than 1.7 rows per visible Gaussian (all-gather moves G)
+    visible = int((ref["radii"] > 0).sum())
+    assert visible <= int(v["cmat"].sum()) <= 1.7 * visible, (int(v["cmat"].sum()), visible)
+    for k in ("means3D", "means2D", "shs", "opacities", "scales", "rotations"):
+        e = hz.rel_err(v["g_" + k], ref["g_" + k])
+        assert e <= 1e-4, (k, e)
+
+
+def test_partition_matches_host_arithmetic():
+    """surfel_shard_partition against the same integer arithmetic in numpy, incl. empty tiles and G > busy tiles."""
+    from streetunveiler_b200.sharded import NativeBackend, COST_BASE
+    be = NativeBackend()
+    cam = syn.make_camera(1920, 1280, 2055.0, 2055.0)
+    s = hz._settings(hz.ours_module(), cam, torch.zeros(3), 0, 1.0, torch.device("cuda"))
+    n = 120 * 80
+    g = torch.Generator().manual_seed(3)
+    for case, G in [("random", 8), ("spike", 5), ("empty", 4), ("random", 16), ("random", 1)]:
+        if case == "random":
+            hist = torch.randint(0, 3000, (n,), generator=g)
+        elif case == "spike":
+            hist = torch.zeros(n, dtype=torch.int64)
+            hist[5000] = 10_000_000
+        else:
+            hist = torch.zeros(n, dtype=torch.int64)
+        cuts, wr = be.partition(s, hist.to(torch.int32).cuda(), G)
+        cost = hist.numpy().astype(np.int64) + COST_BASE
+        excl = np.cumsum(cost) - cost
+        rank_of = np.minimum(excl * G // int(cost.sum()), G - 1)
+        want_cuts = [int((rank_of < k).sum()) for k in range(G)] + [n]
+        want_R = [int(hist.numpy()[want_cuts[k]:want_cuts[k + 1]].sum()) for k in range(G)]
+        assert cuts.cpu().tolist() == want_cuts, (case, G)
+        assert wr.cpu().tolist() == want_R, (case, G)
+
+
+def test_grad_accumulate_sums_rows_of_shared_gaussians():
+    from streetunveiler_b200.sharded import NativeBackend, GREC_FLOATS
+    be = NativeBackend()
+    g = torch.Generator().manual_seed(1)
+    P, n = 1000, 1700
+    src = torch.randint(0, P, (n,), generator=g)
+    rows = torch.randn(n, GREC_FLOATS, generator=g)
+    got = be.grad_accumulate(P, rows.cuda(), src.to(torch.int32).cuda()).cpu()
+    want = torch.zeros(P, GREC_FLOATS).index_add_(0, src, rows)
+    assert torch.allclose(got, want, atol=1e-5)
+    assert float(be.grad_accumulate(P, rows[:0].cuda(), src[:0].to(torch.int32).cuda()).abs().max()) == 0.0
