@@ -617,7 +617,7 @@ def run_ours(args):
         from streetunveiler_b200 import sharded as _sh
         selfcheck = {"weak_scene": selfcheck_and_single(mod, wl, sharded, world, rank, device, args.steps, args.warmup,
                                                         time_single=strong_only)}
-        if not strong_only:
+        if not strong_only and not args.no_strong:
             del step, leaves, m2, state
             wl2 = Workload((STRONG_TOTAL // world) * world, 2, world, rank, device)
             step2, leaves2, m22, state2 = make_step(mod, wl2, sharded)

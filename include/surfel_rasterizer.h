@@ -198,11 +198,14 @@ SURFEL_API int surfel_shard_compact(
 /* hist: uint32[tiles] (tiles = ceil(W/16) * ceil(H/16)), overwritten. */
 SURFEL_API int surfel_shard_tile_hist(int P, int width, int height, const float *records, const int *radii,
                                       uint32_t *hist, void *stream);
-/* hist: the all-reduced histogram.  cost of a tile = its instance count + cost_base.  cuts: DEVICE int32[G+1],
- * window_num_rendered: DEVICE int64[G]; temp: surfel_shard_partition_bytes(width, height).  1 <= G <= 16. */
+/* hist: the all-reduced histogram.  cost of a tile = its instance count + cost_base; rank k receives the share
+ * shares[k] / sum(shares) of the total cost (shares: HOST float[G] or NULL = equal shares; the host side adapts them
+ * from the ranks' measured blend times).  cuts: DEVICE int32[G+1], window_num_rendered: DEVICE int64[G];
+ * temp: surfel_shard_partition_bytes(width, height).  1 <= G <= 16. */
 SURFEL_API size_t surfel_shard_partition_bytes(int width, int height);
-SURFEL_API int surfel_shard_partition(int width, int height, int G, const uint32_t *hist, int cost_base, char *temp,
-                                      int *cuts, int64_t *window_num_rendered, void *stream);
+SURFEL_API int surfel_shard_partition(int width, int height, int G, const uint32_t *hist, int cost_base,
+                                      const float *shares, char *temp, int *cuts, int64_t *window_num_rendered,
+                                      void *stream);
 /* temp: surfel_shard_route_bytes(P, G), shared by the two calls.  send_counts: DEVICE int32[G].
  * send_rows: [sum(send_counts), 28] fp32, segment d = rows for rank d; send_src[row] = local Gaussian index. */
 SURFEL_API size_t surfel_shard_route_bytes(int P, int G);

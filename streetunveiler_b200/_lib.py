@@ -37,7 +37,7 @@ SIGNATURES = {
     "surfel_shard_compact": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_shard_tile_hist": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "surfel_shard_partition_bytes": (C.c_size_t, [_i, _i]),
-    "surfel_shard_partition": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "surfel_shard_partition": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "surfel_shard_route_bytes": (C.c_size_t, [_i, _i]),
     "surfel_shard_route_count": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_shard_route_scatter": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

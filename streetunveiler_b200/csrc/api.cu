@@ -744,14 +744,14 @@ size_t surfel_shard_partition_bytes(int width, int height)
     return partition_temp_bytes(((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y));
 }
 
-int surfel_shard_partition(int width, int height, int G, const uint32_t *hist, int cost_base, char *temp, int *cuts,
-                           int64_t *window_num_rendered, void *stream)
+int surfel_shard_partition(int width, int height, int G, const uint32_t *hist, int cost_base, const float *shares,
+                           char *temp, int *cuts, int64_t *window_num_rendered, void *stream)
 {
     if (width <= 0 || height <= 0 || G < 1 || G > MAX_RANKS || cost_base < 0)
         return fail("surfel_shard_partition", "bad sizes (1 <= G <= 16)");
     if (!hist || !temp || !cuts || !window_num_rendered) return fail("surfel_shard_partition", "NULL required pointer");
     const int ntiles = ((width + TILE_X - 1) / TILE_X) * ((height + TILE_Y - 1) / TILE_Y);
-    launch_partition(ntiles, G, hist, (uint32_t)cost_base, temp, cuts, reinterpret_cast<long long *>(window_num_rendered),
+    launch_partition(ntiles, G, hist, (uint32_t)cost_base, shares, temp, cuts, reinterpret_cast<long long *>(window_num_rendered),
                      static_cast<cudaStream_t>(stream));
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("surfel_shard_partition", e);

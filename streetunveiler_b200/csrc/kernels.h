@@ -57,8 +57,8 @@ cudaError_t run_compact_visible(int P, const int *radii, const float *rec, const
 // ---- multi-GPU exchange (exchange.cu) ----
 void launch_tile_hist(int P, int gx, int gy, const float *rec, const int *radii, uint32_t *hist, cudaStream_t stream);
 size_t partition_temp_bytes(int ntiles);
-void launch_partition(int ntiles, int G, const uint32_t *hist, uint32_t cost_base, char *temp, int *cuts,
-                      long long *window_R, cudaStream_t stream);
+void launch_partition(int ntiles, int G, const uint32_t *hist, uint32_t cost_base, const float *shares_host,
+                      char *temp, int *cuts, long long *window_R, cudaStream_t stream);
 size_t route_temp_bytes(int P, int G);
 cudaError_t run_route_count(int P, int gx, int gy, int G, const float *rec, const int *radii, const int *cuts,
                             char *temp, int *send_counts, cudaStream_t stream);

@@ -48,7 +48,7 @@ REC_FLOATS = 24
 GREC_FLOATS = 20
 XROW_FLOATS = 28     # exchanged row: record + depth key + radius + 2 pad words (csrc/common.cuh)
 TILE = 16
-COST_BASE = 16       # per-tile constant of the partition's cost model, in units of one tile instance
+COST_BASE = 512      # per-tile constant of the partition's cost model, in units of one tile instance (prior; the feedback of _Balancer does the rest)
 
 # SURFEL_SHARD_TIMING=1: synchronise around every phase and record wall-clock per phase and call (diagnostics only)
 import os as _os
@@ -161,14 +161,17 @@ class NativeBackend:
                                                       C.c_void_p(hist.data_ptr()), self._stream()), "surfel_shard_tile_hist")
         return hist
 
-    def partition(self, s, hist, world):
-        """-> one int64 device tensor [G + 1 + G]: cuts (tile ids) followed by every range's instance count."""
+    def partition(self, s, hist, world, shares=None, cost_base=None):
+        """-> (cuts int32[G + 1] tile ids, window_R int64[G] instance count of every range), both on the device.
+        shares: G positive floats, the fraction of the frame's cost every rank should receive (None: equal)."""
         W, H, dev = s.image_width, s.image_height, hist.device
         tmp = torch.empty((self._lib.size(self.L.surfel_shard_partition_bytes(W, H), "surfel_shard_partition_bytes"),),
                           dtype=torch.uint8, device=dev)
         cuts = torch.empty((world + 1,), dtype=torch.int32, device=dev)
         wr = torch.empty((world,), dtype=torch.int64, device=dev)
-        self._lib.check(self.L.surfel_shard_partition(W, H, world, C.c_void_p(hist.data_ptr()), COST_BASE,
+        sh = None if shares is None else (C.c_float * world)(*[float(x) for x in shares])
+        self._lib.check(self.L.surfel_shard_partition(W, H, world, C.c_void_p(hist.data_ptr()),
+                                                      COST_BASE if cost_base is None else int(cost_base), sh,
                                                       C.c_void_p(tmp.data_ptr()), C.c_void_p(cuts.data_ptr()),
                                                       C.c_void_p(wr.data_ptr()), self._stream()), "surfel_shard_partition")
         return cuts, wr
@@ -256,11 +259,70 @@ class NativeBackend:
 
 
 # ----------------------------------------------------------------------------------------------------
+class _Balancer:
+    """Feedback for the screen partition.  The blend time of a tile range is not proportional to its instance count
+    (sparse regions cost more per instance than saturated ones, and a range cannot finish before its longest tile
+    list), so every rank measures its own window time (forward sort+bin+blend and backward blend, CUDA events) and the
+    shares of the cost histogram that the ranks receive are corrected multiplicatively:
+        share_k <- share_k * (mean time / time_k) ** gain, normalised.
+    The times travel with the per-step all-gather of the send counts, so every rank sees the same numbers and derives
+    the same shares; a measurement is applied two steps later (its events are then complete on every rank without an
+    extra synchronisation) to the shares it was measured under.  Only WHO blends a tile depends on this, never a result.
+    """
+
+    def __init__(self, world: int, gain: float = 0.7, floor: float = 0.02):
+        self.world, self.gain, self.floor = world, gain, floor
+        self.shares = [1.0 / world] * world
+        self.step = 0
+        self.records = {}     # step -> {"shares": [...], "ev": [e0, e1, e2, e3]}
+
+    def begin_step(self):
+        self.step += 1
+        self.records[self.step] = {"shares": list(self.shares), "ev": [None] * 4}
+        for k in [k for k in self.records if k < self.step - 4]:
+            del self.records[k]
+        return self.step
+
+    def mark(self, step, i):
+        rec = self.records.get(step)
+        if rec is not None and torch.cuda.is_available():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            rec["ev"][i] = e
+
+    def report(self):
+        """(step, microseconds) of this rank's measurement that is two steps old (0 us if there is none)."""
+        k = self.step - 2
+        rec = self.records.get(k)
+        if rec is None or rec["ev"][0] is None or rec["ev"][1] is None:
+            return k, 0
+        try:
+            ms = rec["ev"][0].elapsed_time(rec["ev"][1])
+            if rec["ev"][2] is not None and rec["ev"][3] is not None:
+                ms += rec["ev"][2].elapsed_time(rec["ev"][3])
+        except RuntimeError:      # an event that never completed (e.g. backward skipped mid-way)
+            return k, 0
+        return k, max(int(ms * 1000.0), 1)
+
+    def update(self, step, times_us):
+        rec = self.records.get(step)
+        if rec is None or any(t <= 0 for t in times_us):
+            return
+        mean = sum(times_us) / len(times_us)
+        new = [s * (mean / t) ** self.gain for s, t in zip(rec["shares"], times_us)]
+        tot = sum(new)
+        new = [max(x / tot, self.floor / self.world) for x in new]
+        tot = sum(new)
+        self.shares = [x / tot for x in new]
+
+
 class _ShardedRasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, shs, opacities, scales, rotations, settings, backend, group, check_replicated):
+    def forward(ctx, means3D, means2D, shs, opacities, scales, rotations, settings, backend, group, check_replicated,
+                balancer):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         P = means3D.shape[0]
+        step_id = balancer.begin_step() if balancer is not None else 0
         with _phase("fwd preprocess"):
             radii, rec, keys, clamped = backend.shard_preprocess(settings, means3D.contiguous(), shs.contiguous(),
                                                                  opacities.contiguous(), scales.contiguous(),
@@ -268,32 +330,43 @@ class _ShardedRasterize(torch.autograd.Function):
         with _phase("fwd partition (hist all-reduce, cuts)"):
             hist = backend.tile_hist(settings, rec, radii)
             dist.all_reduce(hist, group=group)
-            cuts, window_R = backend.partition(settings, hist, world)
+            cuts, window_R = backend.partition(settings, hist, world, balancer.shares if balancer is not None else None)
         with _phase("fwd route counts + host sync"):
             route_state, send_counts = backend.route_count(settings, rec, radii, cuts, world)
-            counts_all = _all_gather_rows(send_counts, group)                      # [G * G]: row s = what rank s sends
-            host = torch.cat([counts_all.to(torch.int64), cuts.to(torch.int64), window_R.to(torch.int64)]).cpu()
-            cmat = host[:world * world].view(world, world)
-            cuts_h = host[world * world:world * world + world + 1].tolist()
-            R = int(host[world * world + world + 1 + rank])
+            rep_step, rep_us = balancer.report() if balancer is not None else (0, 0)
+            extra = torch.tensor([rep_us], dtype=send_counts.dtype).to(send_counts.device, non_blocking=True)
+            gathered = _all_gather_rows(torch.cat([send_counts, extra]), group).view(world, world + 1)
+            host = torch.cat([gathered.flatten().to(torch.int64), cuts.to(torch.int64), window_R.to(torch.int64)]).cpu()
+            gmat = host[:world * (world + 1)].view(world, world + 1)
+            cmat = gmat[:, :world]
+            cuts_h = host[world * (world + 1):world * (world + 1) + world + 1].tolist()
+            R = int(host[world * (world + 1) + world + 1 + rank])
             in_splits = cmat[rank].tolist()
             out_splits = cmat[:, rank].tolist()
+            if balancer is not None:
+                balancer.update(rep_step, gmat[:, world].tolist())
         with _phase("fwd scatter + all-to-all"):
             send_rows, send_src = backend.route_scatter(rec, radii, keys, route_state, send_counts, int(sum(in_splits)),
                                                         world)
             recv_rows = _all_to_all_rows(send_rows, in_splits, out_splits, group)
             del send_rows
         with _phase("fwd window (sort+bin+blend)"):
+            if balancer is not None:
+                balancer.mark(step_id, 0)
             rec_w, radii_w, keys_w = backend.unpack(recv_rows)
             del recv_rows
             planes, state = backend.window_forward(settings, rec_w, radii_w, keys_w, int(cuts_h[rank]),
                                                    int(cuts_h[rank + 1]), R)
+            if balancer is not None:
+                balancer.mark(step_id, 1)
         with _phase("fwd image all-reduce"):
             dist.all_reduce(planes, group=group)               # every rank wrote only its tiles
-        LAST_INFO.update(cuts=cuts_h, send=in_splits, recv=out_splits, num_rendered=R, shard=P)
+        LAST_INFO.update(cuts=cuts_h, send=in_splits, recv=out_splits, num_rendered=R, shard=P,
+                         shares=list(balancer.shares) if balancer is not None else None)
         ctx.settings, ctx.backend, ctx.group, ctx.state = settings, backend, group, state
         ctx.splits = (in_splits, out_splits)
         ctx.check_replicated = check_replicated
+        ctx.balancer, ctx.step_id = balancer, step_id
         ctx.num_rendered = R
         ctx.save_for_backward(means3D, shs, scales, rotations, radii, rec, clamped, rec_w, send_src)
         ctx.mark_non_differentiable(radii)
@@ -312,13 +385,18 @@ class _ShardedRasterize(torch.autograd.Function):
             if not torch.equal(lo, hi):
                 raise RuntimeError("ShardedRasterizer: upstream gradients differ between ranks (replicated-loss contract)")
         with _phase("bwd window blend"):
+            if ctx.balancer is not None:
+                ctx.balancer.mark(ctx.step_id, 2)
             grows = backend.window_backward(s, rec_w, ctx.state, g_color.contiguous(), g_others.contiguous())
+            if ctx.balancer is not None:
+                ctx.balancer.mark(ctx.step_id, 3)
         with _phase("bwd all-to-all"):
             back = _all_to_all_rows(grows, out_splits, in_splits, group)
         with _phase("bwd per-Gaussian"):
             gacc = backend.grad_accumulate(means3D.shape[0], back, send_src)
             g = backend.shard_backward(s, means3D, shs, scales, rotations, radii, rec, clamped, gacc, None)
-        return g["means3D"], g["means2D"], g["shs"], g["opacities"], g["scales"], g["rotations"], None, None, None, None
+        return (g["means3D"], g["means2D"], g["shs"], g["opacities"], g["scales"], g["rotations"], None, None, None, None,
+                None)
 
 
 class ShardedRasterizer:
@@ -327,11 +405,12 @@ class ShardedRasterizer:
     ``rasterizer(means3D, means2D, opacities, shs, scales, rotations, settings) -> (color, radii, allmap)``
     where color / allmap are the full images (identical on every rank) and radii belongs to the shard.
     The upstream gradients given to ``backward`` must be identical on every rank (module docstring);
-    ``check_replicated=True`` verifies that on every backward.
+    ``check_replicated=True`` verifies that on every backward.  ``balance=True`` (default) adapts the screen
+    partition to the ranks' measured blend times (class _Balancer); results do not depend on it.
     """
 
     def __init__(self, world: Optional[int] = None, rank: Optional[int] = None, backend=None, group=None,
-                 check_replicated: bool = False):
+                 check_replicated: bool = False, balance: bool = True):
         self.group = group
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
@@ -339,7 +418,8 @@ class ShardedRasterizer:
             raise ValueError("at most 16 ranks per scene (csrc/common.cuh MAX_RANKS)")
         self.backend = backend if backend is not None else NativeBackend()
         self.check_replicated = check_replicated
+        self.balancer = _Balancer(self.world) if balance else None
 
     def __call__(self, means3D, means2D, opacities, shs, scales, rotations, settings):
         return _ShardedRasterize.apply(means3D, means2D, shs, opacities, scales, rotations, settings, self.backend,
-                                       self.group, self.check_replicated)
+                                       self.group, self.check_replicated, self.balancer)

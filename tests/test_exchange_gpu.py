@@ -83,7 +83,7 @@ def test_virtual_ranks_equal_single_gpu(G, P, mode):
     assert sum(v["window_R"]) == ref["num_rendered"]
     assert v["cuts"][0] == 0 and v["cuts"][-1] == 60 * 40 and all(a <= b for a, b in zip(v["cuts"], v["cuts"][1:]))
     # cost balance: no range holds more than 1.6x its share of the instances (+ the constant per tile)
-    cost = [r + 16 * (b - a) for r, a, b in zip(v["window_R"], v["cuts"], v["cuts"][1:])]
+    cost = [r + 512 * (b - a) for r, a, b in zip(v["window_R"], v["cuts"], v["cuts"][1:])]
     assert max(cost) <= 1.6 * sum(cost) / G, (cost, v["cuts"])
     # a record goes to few ranks: the exchange moves less than 1.7 rows per visible Gaussian (all-gather moves G)
     visible = int((ref["radii"] > 0).sum())
@@ -101,7 +101,8 @@ def test_partition_matches_host_arithmetic():
     s = hz._settings(hz.ours_module(), cam, torch.zeros(3), 0, 1.0, torch.device("cuda"))
     n = 120 * 80
     g = torch.Generator().manual_seed(3)
-    for case, G in [("random", 8), ("spike", 5), ("empty", 4), ("random", 16), ("random", 1)]:
+    for case, G, shares in [("random", 8, None), ("spike", 5, None), ("empty", 4, None), ("random", 16, None),
+                            ("random", 1, None), ("random", 4, [0.1, 0.4, 0.2, 0.3]), ("random", 3, [0.0, 1.0, 1.0])]:
         if case == "random":
             hist = torch.randint(0, 3000, (n,), generator=g)
         elif case == "spike":
@@ -109,14 +110,21 @@ def test_partition_matches_host_arithmetic():
             hist[5000] = 10_000_000
         else:
             hist = torch.zeros(n, dtype=torch.int64)
-        cuts, wr = be.partition(s, hist.to(torch.int32).cuda(), G)
+        cuts, wr = be.partition(s, hist.to(torch.int32).cuda(), G, shares)
         cost = hist.numpy().astype(np.int64) + COST_BASE
         excl = np.cumsum(cost) - cost
-        rank_of = np.minimum(excl * G // int(cost.sum()), G - 1)
+        total = int(cost.sum())
+        sh = [1.0] * G if shares is None else [np.float32(x).item() for x in shares]
+        acc, bounds = 0.0, []
+        for k in range(G):                       # the launcher's fixed-point targets and the kernel's ceil(total * t / 2^32)
+            t = 0 if k == 0 else int(acc / sum(sh) * 4294967296.0 + 0.5)
+            bounds.append((total * t + (1 << 32) - 1) >> 32)
+            acc += sh[k]
+        rank_of = np.array([sum(1 for k in range(1, G) if int(e) >= bounds[k]) for e in excl])
         want_cuts = [int((rank_of < k).sum()) for k in range(G)] + [n]
         want_R = [int(hist.numpy()[want_cuts[k]:want_cuts[k + 1]].sum()) for k in range(G)]
-        assert cuts.cpu().tolist() == want_cuts, (case, G)
-        assert wr.cpu().tolist() == want_R, (case, G)
+        assert cuts.cpu().tolist() == want_cuts, (case, G, shares)
+        assert wr.cpu().tolist() == want_R, (case, G, shares)
 
 
 def test_grad_accumulate_sums_rows_of_shared_gaussians():

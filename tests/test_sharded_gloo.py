@@ -55,10 +55,12 @@ class ToyBackend:
     def tile_hist(self, s, rec, radii):
         return _tile_cover(rec, radii).sum(0).to(torch.int32)
 
-    def partition(self, s, hist, world):
+    def partition(self, s, hist, world, shares=None):
         cost = hist.to(torch.int64) + sharded.COST_BASE
         excl = torch.cumsum(cost, 0) - cost
-        rank_of = torch.clamp(excl * world // int(cost.sum()), max=world - 1)
+        shares = [1.0 / world] * world if shares is None else shares
+        target = torch.cumsum(torch.tensor([0.0] + list(shares[:-1]), dtype=torch.float64), 0) / sum(shares)   # [G]
+        rank_of = (excl[:, None].double() / float(cost.sum()) >= target[None, 1:]).sum(1)
         cuts = torch.tensor([int((rank_of < k).sum()) for k in range(world)] + [GX * GY], dtype=torch.int32)
         window_R = torch.tensor([int(hist[int(cuts[k]):int(cuts[k + 1])].sum()) for k in range(world)], dtype=torch.int64)
         return cuts, window_R
