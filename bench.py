@@ -648,7 +648,8 @@ def run_ours(args):
         "higher_is_better": True,
         "scaling": "strong" if args.total else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": make_config(P_total, wl.P, seed, world, R, P_vis, wl.crc, strong=strong_only),
+        "config": dict(make_config(P_total, wl.P, seed, world, R, P_vis, wl.crc, strong=strong_only),
+                       **({"image_exchange": sharded.backend.image_exchange} if sharded is not None else {})),
         "clocks": clocks,
         "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3), "step_stats": e2e_info},

@@ -231,6 +231,16 @@ SURFEL_API int surfel_window_render(
     const float *background, const float *records, const int *radii,
     char *window_buffer, char *binning_buffer, char *image_buffer,
     float *out_color, float *out_others, void *stream, int debug);
+/* Same, with the image exchange fused into the blend: the ten planes of the window's pixels are stored into the
+ * [10,H,W] fp32 buffers peer_planes[0..n_peers) (HOST array of DEVICE addresses that this GPU can store to: its own
+ * buffer and its peers' over NVLink; or, with multicast != 0, ONE NVSwitch multicast address that reaches all of
+ * them, written with multimem.st).  Pixels outside the window are not touched.  The caller synchronises the ranks
+ * (a barrier) before anyone reads. */
+SURFEL_API int surfel_window_render_peers(
+    int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
+    const float *background, const float *records, const int *radii,
+    char *window_buffer, char *binning_buffer, char *image_buffer,
+    int n_peers, float *const *peer_planes, int multicast, void *stream, int debug);
 SURFEL_API int surfel_window_backward(
     int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
     const float *background, const float *records, char *binning_buffer, char *image_buffer,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "surfel_window_bytes": (C.c_size_t, [_i]),
     "surfel_window_prepare": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _i]),
     "surfel_window_render": (_i, [_i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "surfel_window_render_peers": (_i, [_i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i]),
     "surfel_window_backward": (_i, [_i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "surfel_shard_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -845,24 +845,27 @@ int surfel_window_prepare(int P_total, int width, int height, int tile_lo, int t
     return 0;
 }
 
-int surfel_window_render(int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
-                         const float *background, const float *records, const int *radii, char *window_buffer,
-                         char *binning_buffer, char *image_buffer, float *out_color, float *out_others, void *stream,
-                         int debug)
+static int window_render_impl(const char *where, int P_total, int width, int height, int tile_lo, int tile_hi,
+                              int64_t num_rendered, const float *background, const float *records, const int *radii,
+                              char *window_buffer, char *binning_buffer, char *image_buffer, float *out_color,
+                              float *out_others, int n_peers, float *const *peer_planes, int multicast, void *stream,
+                              int debug)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (P_total < 0 || width <= 0 || height <= 0 || num_rendered < 0 || tile_lo < 0 || tile_hi < tile_lo)
-        return fail("surfel_window_render", "bad sizes");
-    if (!background || !image_buffer || !out_color || !out_others) return fail("surfel_window_render", "NULL required pointer");
-    if (P_total > 0 && (!records || !radii || !window_buffer)) return fail("surfel_window_render", "NULL geometry");
-    if (num_rendered > 0 && !binning_buffer) return fail("surfel_window_render", "NULL binning_buffer");
+        return fail(where, "bad sizes");
+    if (!background || !image_buffer) return fail(where, "NULL required pointer");
+    if (n_peers == 0 && (!out_color || !out_others)) return fail(where, "NULL required pointer");
+    if (n_peers < 0 || n_peers > MAX_RANKS || (n_peers > 0 && !peer_planes)) return fail(where, "bad peer list");
+    if (P_total > 0 && (!records || !radii || !window_buffer)) return fail(where, "NULL geometry");
+    if (num_rendered > 0 && !binning_buffer) return fail(where, "NULL binning_buffer");
     const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+    if (tile_hi > gx * gy) return fail(where, "tile range exceeds the tile grid");
     ImageView iv = carve_image(image_buffer, width, height);
     WindowView w{};
     BinView bv{};
     if (P_total > 0) w = carve_window(window_buffer, P_total, depth_sort_temp_bytes(P_total));
     if (num_rendered > 0) bv = carve_bin(binning_buffer, num_rendered, tile_sort_temp_bytes(num_rendered));
-    if (tile_hi > gx * gy) return fail("surfel_window_render", "tile range exceeds the tile grid");
     CK("tile binning", run_tile_binning(P_total, num_rendered, gx, gy, tile_lo, tile_hi, records, radii,
                                         w.idx_sorted, w.offsets, bv.keys_unsorted, bv.vals_unsorted, bv.keys_sorted,
                                         bv.point_list, iv.ranges, iv.tile_order, bv.cub_temp, bv.cub_temp_bytes, st));
@@ -872,9 +875,35 @@ int surfel_window_render(int P_total, int width, int height, int tile_lo, int ti
     r.ranges = iv.ranges; r.tile_order = iv.tile_order; r.point_list = bv.point_list; r.rec = records; r.bg = background;
     r.final_T = iv.final_T; r.n_contrib = iv.n_contrib; r.tile_max_contrib = iv.tile_max_contrib;
     r.out_color = out_color; r.out_others = out_others; r.subtile_cull = g_subtile_cull;
+    r.n_peers = n_peers; r.peer_multicast = multicast;
+    for (int q = 0; q < n_peers; q++) {
+        if (!peer_planes[q] || !aligned(peer_planes[q], 4)) return fail(where, "bad peer plane pointer");
+        r.peer_planes[q] = peer_planes[q];
+    }
     launch_render_fwd(r, st);
     STAGE("render forward");
     return 0;
+}
+
+int surfel_window_render(int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
+                         const float *background, const float *records, const int *radii, char *window_buffer,
+                         char *binning_buffer, char *image_buffer, float *out_color, float *out_others, void *stream,
+                         int debug)
+{
+    return window_render_impl("surfel_window_render", P_total, width, height, tile_lo, tile_hi, num_rendered, background,
+                              records, radii, window_buffer, binning_buffer, image_buffer, out_color, out_others, 0,
+                              nullptr, 0, stream, debug);
+}
+
+int surfel_window_render_peers(int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,
+                               const float *background, const float *records, const int *radii, char *window_buffer,
+                               char *binning_buffer, char *image_buffer, int n_peers, float *const *peer_planes,
+                               int multicast, void *stream, int debug)
+{
+    if (n_peers < 1) return fail("surfel_window_render_peers", "needs at least one destination");
+    return window_render_impl("surfel_window_render_peers", P_total, width, height, tile_lo, tile_hi, num_rendered,
+                              background, records, radii, window_buffer, binning_buffer, image_buffer, nullptr, nullptr,
+                              n_peers, peer_planes, multicast, stream, debug);
 }
 
 int surfel_window_backward(int P_total, int width, int height, int tile_lo, int tile_hi, int64_t num_rendered,

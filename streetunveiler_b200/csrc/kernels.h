@@ -99,6 +99,10 @@ struct RenderFwdArgs {
     float *out_color, *out_others;
     int subtile_cull;
     int n_classes = 0;  // > 0: class-probability pass (out_color = [n_classes,H,W], bg = [n_classes], out_others unused)
+    // multi-GPU: store the window's pixels into these [10,H,W] plane buffers (one per rank, or ONE multicast address)
+    // instead of out_color / out_others
+    int n_peers = 0, peer_multicast = 0;
+    float *peer_planes[16] = {};
 };
 void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream);
 

@@ -27,9 +27,28 @@ namespace surfel {
 //   red, the pass accumulates w into the label's channel -- bit for bit what the reference gets from one-hot
 //   "colours" (1 * w and 0 * w are exact) -- for up to MAX_CLASSES channels in ONE traversal of the lists, and writes
 //   only the class images plus the per-pixel state the backward needs (T, last contributor).
-template <bool CULL, bool CLASSES>
+// PEERS = true (multi-GPU path, exchange fused into the blend): the ten output planes of this rank's tiles are stored
+// straight into the image buffers of ALL ranks over NVLink -- either one `multimem.st` per value through the NVSwitch
+// multicast address of the symmetric buffer (the switch replicates it to every GPU), or one plain store per peer.  The
+// stores are fire-and-forget and overlap with the blend of the other tiles; a cross-rank barrier after the kernel
+// replaces the all-reduce of ten mostly-zero planes (streetunveiler_b200/sharded.py).
+struct PeerPlanes {
+    float *base[MAX_RANKS];   // [10,H,W] planes of every destination (colour 0..2, allmap 3..9)
+    int n;                    // number of destinations (1 with multicast)
+    int multicast;            // base[0] is a multicast address: use multimem.st
+};
+
+__device__ __forceinline__ void peer_store(float *p, const float v, const int multicast)
+{
+    if (multicast)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    else
+        *p = v;
+}
+
+template <bool CULL, bool CLASSES, bool PEERS = false>
 __global__ void __launch_bounds__(TILE_THREADS)
-render_fwd_kernel(const int n_classes,
+render_fwd_kernel(const PeerPlanes peers, const int n_classes,
                   const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
                   const uint2 *__restrict__ ranges,
                   const uint32_t *__restrict__ point_list, const float *__restrict__ rec,
@@ -194,6 +213,16 @@ render_fwd_kernel(const int n_classes,
         final_T[pix_id + HW] = M1;
         final_T[pix_id + 2 * HW] = M2;
         n_contrib[pix_id + HW] = median_contributor;
+        if constexpr (PEERS) {
+            const float v[10] = {C[0] + T * bg[0], C[1] + T * bg[1], C[2] + T * bg[2], Dacc, 1 - T, N[0], N[1], N[2],
+                                 median_depth, distortion};
+            for (int q = 0; q < peers.n; q++) {
+                float *o = peers.base[q] + pix_id;
+#pragma unroll
+                for (int k = 0; k < 10; k++) peer_store(o + k * HW, v[k], peers.multicast);
+            }
+            return;
+        }
         out_color[pix_id] = C[0] + T * bg[0];
         out_color[pix_id + HW] = C[1] + T * bg[1];
         out_color[pix_id + 2 * HW] = C[2] + T * bg[2];
@@ -207,12 +236,18 @@ render_fwd_kernel(const int n_classes,
     }
 }
 
-template <bool CULL, bool CLASSES>
+template <bool CULL, bool CLASSES, bool PEERS = false>
 static void launch_fwd(const RenderFwdArgs &a, const int tiles, cudaStream_t stream)
 {
-    auto k = render_fwd_kernel<CULL, CLASSES>;
+    auto k = render_fwd_kernel<CULL, CLASSES, PEERS>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileRing<FWD_STAGES>));  // per device, cheap
-    k<<<tiles, TILE_THREADS, sizeof(TileRing<FWD_STAGES>), stream>>>(a.n_classes, a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list,
+    PeerPlanes peers{};
+    if (PEERS) {
+        peers.n = a.n_peers;
+        peers.multicast = a.peer_multicast;
+        for (int q = 0; q < a.n_peers && q < MAX_RANKS; q++) peers.base[q] = a.peer_planes[q];
+    }
+    k<<<tiles, TILE_THREADS, sizeof(TileRing<FWD_STAGES>), stream>>>(peers, a.n_classes, a.W, a.H, a.gx, a.tile_order, a.ranges, a.point_list,
                                                                       a.rec, a.bg, a.final_T, a.n_contrib, a.tile_max_contrib,
                                                                       a.out_color, a.out_others);
 }
@@ -223,6 +258,8 @@ void launch_render_fwd(const RenderFwdArgs &a, cudaStream_t stream)
     if (tiles <= 0) return;
     if (a.n_classes > 0)
         launch_fwd<true, true>(a, tiles, stream);
+    else if (a.n_peers > 0)
+        launch_fwd<true, false, true>(a, tiles, stream);
     else if (a.subtile_cull)
         launch_fwd<true, false>(a, tiles, stream);
     else

@@ -20,8 +20,11 @@ partitions the SCREEN, and exchanges only *projected* data -- and only with the 
             5. every rank depth-sorts, bins and blends what it received for its own tiles
                (surfel_window_unpack / _prepare / _render): same lists, order and arithmetic per pixel as
                on one GPU
-            6. all-reduce(sum) of the ten image planes (each pixel has exactly one non-zero summand, so
-               the sum is exact)
+            6. image exchange fused into the blend: every rank's kernel stores the ten planes of its tiles
+               straight into symmetric buffers of ALL ranks (NVSwitch multicast `multimem.st`, or one store
+               per peer over NVLink), then one cross-rank barrier (class PeerImages).  Fallback where no
+               peer mapping exists (and on CPU/gloo): all-reduce(sum) of the planes -- each pixel has
+               exactly one non-zero summand, so the sum is exact
   backward  7. every rank back-propagates its tiles into 80-B gradient rows of the records it received
                                                                      (surfel_window_backward)
             8. all-to-all of the gradient rows back along the same routes; the owner sums the rows of a
@@ -105,6 +108,49 @@ def pad_rows(x: torch.Tensor, n: int, value=0) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------
+# image exchange fused into the blend kernel: symmetric [10,H,W] buffers that every rank's kernel stores into
+# ----------------------------------------------------------------------------------------------------
+IMAGE_EXCHANGE = _os.environ.get("SURFEL_IMAGE_EXCHANGE", "auto")   # auto | multicast | peers | allreduce
+
+
+class PeerImages:
+    """Two symmetric-memory image buffers per resolution (torch.distributed._symmetric_memory: CUDA VMM allocations
+    mapped into every rank of the node, plus an NVSwitch multicast mapping when the fabric has one).  The forward
+    blend kernel of every rank stores the ten planes of ITS tiles into all ranks' buffers -- one ``multimem.st`` per
+    value to the multicast address, or one store per peer -- so the image exchange overlaps with the blend and the
+    all-reduce of ten mostly-zero planes (98 MB at 1920x1280, ring: 2 x 7/8 of it per rank) disappears.  ``finish``
+    = cross-rank barrier (every store has landed) + copy-out into a private tensor.  Buffers alternate between frames:
+    a rank that runs ahead never writes into a buffer a slower rank may still be copying out of."""
+
+    def __init__(self, H, W, device, group, mode):
+        import torch.distributed._symmetric_memory as symm
+        self.H, self.W, self.frame = H, W, 0
+        g = group if group is not None else dist.group.WORLD
+        self.slots = []
+        for _ in range(2):
+            t = symm.empty((10 * H * W,), dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(t, g)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if mode == "peers" or (mode == "auto" and not mc):
+                ptrs, multicast = [int(x) for x in hdl.buffer_ptrs], 0
+            elif mc:
+                ptrs, multicast = [mc], 1
+            else:
+                raise RuntimeError("no NVSwitch multicast mapping for the symmetric buffer")
+            self.slots.append((t, hdl, ptrs, multicast))
+        self.mode = "multicast" if self.slots[0][3] else "peers"
+
+    def begin(self):
+        self.frame += 1
+        return self.slots[self.frame & 1]
+
+    def finish(self, slot):
+        t, hdl, _, _ = slot
+        hdl.barrier(channel=0)
+        return t.view(10, self.H, self.W).clone()
+
+
+# ----------------------------------------------------------------------------------------------------
 # native backend: the CUDA library through its C ABI
 # ----------------------------------------------------------------------------------------------------
 class NativeBackend:
@@ -112,6 +158,27 @@ class NativeBackend:
         from . import _lib
         self._lib = _lib
         self.L = _lib.lib()
+        self._peer_images = {}
+        self.image_exchange = None      # "multicast" | "peers" | "allreduce" once the first frame ran
+
+    def peer_images(self, s, device, group):
+        """Symmetric image buffers for this resolution, or None -> the caller all-reduces the planes instead
+        (SURFEL_IMAGE_EXCHANGE=allreduce, a world of one, or a node without peer mappings)."""
+        if IMAGE_EXCHANGE == "allreduce" or dist.get_world_size(group) == 1:
+            self.image_exchange = "allreduce"
+            return None
+        key = (s.image_height, s.image_width, device.index)
+        if key not in self._peer_images:
+            try:
+                self._peer_images[key] = PeerImages(s.image_height, s.image_width, device, group, IMAGE_EXCHANGE)
+            except Exception as exc:   # all ranks fail alike (same node, same software): a collective decision
+                import warnings
+                warnings.warn(f"symmetric-memory image exchange unavailable ({type(exc).__name__}: {exc}); "
+                              f"using the NCCL all-reduce of the image planes")
+                self._peer_images[key] = None
+        pi = self._peer_images[key]
+        self.image_exchange = pi.mode if pi is not None else "allreduce"
+        return pi
 
     @staticmethod
     def _p(t):
@@ -206,9 +273,11 @@ class NativeBackend:
                                                     self._stream()), "surfel_window_unpack")
         return rec, radii, keys
 
-    def window_forward(self, s, rec_w, radii_w, keys_w, tile_lo, tile_hi, R):
+    def window_forward(self, s, rec_w, radii_w, keys_w, tile_lo, tile_hi, R, peer_slot=None):
         """Blend the received Gaussians for the tiles [tile_lo, tile_hi); R = the window's instance count (known from
-        the partition).  Planes of other ranks' tiles stay 0 for the all-reduce."""
+        the partition).  Without peer_slot: returns [10,H,W] planes, zero outside the window (for the all-reduce).
+        With peer_slot (PeerImages.begin()): the kernel stores the window's pixels into every rank's buffer; returns
+        None for the planes."""
         L, p, dev = self.L, self._p, rec_w.device
         n, W, H = rec_w.shape[0], s.image_width, s.image_height
         u8 = dict(dtype=torch.uint8, device=dev)
@@ -218,6 +287,13 @@ class NativeBackend:
         self._lib.check(L.surfel_window_prepare(n, W, H, tile_lo, tile_hi, p(rec_w), p(radii_w), p(keys_w), p(win), None,
                                                 st, int(bool(s.debug))), "surfel_window_prepare")
         binb = torch.empty((self._lib.size(L.surfel_binning_bytes(R), "surfel_binning_bytes") if R else 0,), **u8)
+        if peer_slot is not None:
+            _, _, ptrs, multicast = peer_slot
+            arr = (C.c_void_p * len(ptrs))(*ptrs)
+            self._lib.check(L.surfel_window_render_peers(n, W, H, tile_lo, tile_hi, R, p(s.bg), p(rec_w), p(radii_w), p(win),
+                                                         p(binb), p(img), len(ptrs), arr, int(multicast), st,
+                                                         int(bool(s.debug))), "surfel_window_render_peers")
+            return None, (R, binb, img, tile_lo, tile_hi)
         planes = torch.zeros((10, H, W), dtype=torch.float32, device=dev)
         color, others = planes[:3], planes[3:]
         self._lib.check(L.surfel_window_render(n, W, H, tile_lo, tile_hi, R, p(s.bg), p(rec_w), p(radii_w), p(win), p(binb),
@@ -355,12 +431,21 @@ class _ShardedRasterize(torch.autograd.Function):
                 balancer.mark(step_id, 0)
             rec_w, radii_w, keys_w = backend.unpack(recv_rows)
             del recv_rows
-            planes, state = backend.window_forward(settings, rec_w, radii_w, keys_w, int(cuts_h[rank]),
-                                                   int(cuts_h[rank + 1]), R)
+            peers = backend.peer_images(settings, rec.device, group) if hasattr(backend, "peer_images") else None
+            if peers is not None:
+                slot = peers.begin()
+                _, state = backend.window_forward(settings, rec_w, radii_w, keys_w, int(cuts_h[rank]),
+                                                  int(cuts_h[rank + 1]), R, slot)
+            else:
+                planes, state = backend.window_forward(settings, rec_w, radii_w, keys_w, int(cuts_h[rank]),
+                                                       int(cuts_h[rank + 1]), R)
             if balancer is not None:
                 balancer.mark(step_id, 1)
-        with _phase("fwd image all-reduce"):
-            dist.all_reduce(planes, group=group)               # every rank wrote only its tiles
+        with _phase("fwd image exchange (barrier + copy-out | all-reduce)"):
+            if peers is not None:
+                planes = peers.finish(slot)                    # every rank's kernel stored its tiles into every buffer
+            else:
+                dist.all_reduce(planes, group=group)           # every rank wrote only its tiles, the rest is zero
         LAST_INFO.update(cuts=cuts_h, send=in_splits, recv=out_splits, num_rendered=R, shard=P,
                          shares=list(balancer.shares) if balancer is not None else None)
         ctx.settings, ctx.backend, ctx.group, ctx.state = settings, backend, group, state

@@ -68,7 +68,8 @@ def main():
     chk("g_rotations", p["rotations"].grad.cpu().numpy(), ref["g_rotations"][lo:hi], 1e-4)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    print(f"[rank {rank}/{world}] shard [{lo},{hi}) R_window={color.grad_fn.num_rendered} " + " ".join(msgs), flush=True)
+    print(f"[rank {rank}/{world}] shard [{lo},{hi}) R_window={color.grad_fn.num_rendered} image exchange: "
+          f"{rast.backend.image_exchange} " + " ".join(msgs), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if int(flag.item()) != 1:
