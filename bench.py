@@ -649,7 +649,8 @@ def run_ours(args):
         "scaling": "strong" if args.total else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(make_config(P_total, wl.P, seed, world, R, P_vis, wl.crc, strong=strong_only),
-                       **({"image_exchange": sharded.backend.image_exchange} if sharded is not None else {})),
+                       **({"image_exchange": sharded.backend.image_exchange, "row_exchange": sharded.backend.row_exchange}
+                          if sharded is not None else {})),
         "clocks": clocks,
         "e2e": {"value": round(P_total / (ms_e2e * 1e-3) / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3), "step_stats": e2e_info},
@@ -669,6 +670,11 @@ def run_ours(args):
         line["config5_strong"] = strong
     if phases:
         line["shard_phase_ms"] = phases
+    if sharded is not None and sharded.balancer is not None and sharded.balancer.last_times_us:
+        t = sharded.balancer.last_times_us
+        line["shard_balance"] = {"window_fwd_bwd_us_per_rank": t, "imbalance_max_over_mean": round(max(t) / (sum(t) / len(t)), 3),
+                                 "cost_shares": [round(x, 4) for x in sharded.balancer.shares],
+                                 "note": "last measured step of the run (the strong-scaling scene when that leg ran)"}
     if world == 1 and not args.total and not args.no_strong:
         # the N = 1 point of BASELINE configs[4]: the 8M scene on one GPU
         del step, leaves, m2, state

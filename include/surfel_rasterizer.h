@@ -214,6 +214,20 @@ SURFEL_API int surfel_shard_route_count(int P, int width, int height, int G, con
 SURFEL_API int surfel_shard_route_scatter(int P, int G, const float *records, const int *radii,
                                           const uint32_t *depth_keys, char *temp, const int *send_counts,
                                           float *send_rows, uint32_t *send_src, void *stream);
+/* The same scatter with the exchange fused in: rows are stored straight into the destination ranks' receive arrays
+ * (HOST arrays of G DEVICE addresses this GPU can store to -- symmetric memory over NVLink; entry d = rank d's records
+ * [cap,24] fp32 / depth keys [cap] / radii [cap]) starting at row dst_row0[d] (HOST int64[G]: rows that lower ranks
+ * send to d).  No send buffer, no all-to-all, no unpack; the caller synchronises the ranks before anyone reads. */
+SURFEL_API int surfel_shard_route_scatter_peers(int P, int G, const float *records, const int *radii,
+                                                const uint32_t *depth_keys, char *temp, const int *send_counts,
+                                                float *const *dst_records, uint32_t *const *dst_depth_keys,
+                                                int *const *dst_radii, const int64_t *dst_row0, uint32_t *send_src,
+                                                void *stream);
+/* Backward counterpart: gradient rows [n_rows,20] of the received records, in receive order (segment s = the
+ * seg_count[s] rows that came from rank s), are stored into rank s's return buffer dst_rows[s] starting at row
+ * dst_row0[s] -- the position those records have in rank s's send order. */
+SURFEL_API int surfel_window_push_grad_rows(int64_t n_rows, const float *grad_rows, int G, const int64_t *seg_count,
+                                            float *const *dst_rows, const int64_t *dst_row0, void *stream);
 SURFEL_API int surfel_window_unpack(int n, const float *rows, float *records, int *radii, uint32_t *depth_keys,
                                     void *stream);
 /* grad_records [P,20] is zeroed, then grad_records[send_src[j]] += grad_rows[j] for j < n_rows. */

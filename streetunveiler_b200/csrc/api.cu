@@ -787,6 +787,50 @@ int surfel_shard_route_scatter(int P, int G, const float *records, const int *ra
     return e == cudaSuccess ? 0 : fail_cuda("surfel_shard_route_scatter", e);
 }
 
+int surfel_shard_route_scatter_peers(int P, int G, const float *records, const int *radii, const uint32_t *depth_keys,
+                                     char *temp, const int *send_counts, float *const *dst_records,
+                                     uint32_t *const *dst_depth_keys, int *const *dst_radii, const int64_t *dst_row0,
+                                     uint32_t *send_src, void *stream)
+{
+    const char *where = "surfel_shard_route_scatter_peers";
+    if (P < 0 || G < 1 || G > MAX_RANKS) return fail(where, "bad sizes");
+    if (P == 0) return 0;
+    if (!records || !radii || !depth_keys || !temp || !send_counts || !dst_records || !dst_depth_keys || !dst_radii ||
+        !dst_row0 || !send_src)
+        return fail(where, "NULL required pointer");
+    long long row0[MAX_RANKS];
+    for (int d = 0; d < G; d++) {
+        if (!dst_records[d] || !dst_depth_keys[d] || !dst_radii[d] || dst_row0[d] < 0) return fail(where, "bad destination");
+        if (!aligned(dst_records[d], 16)) return fail(where, "destination records must be 16-byte aligned");
+        row0[d] = (long long)dst_row0[d];
+    }
+    if (!aligned(records, 16)) return fail(where, "alignment");
+    const cudaError_t e = run_route_scatter_peers(P, G, records, radii, depth_keys, temp, send_counts, dst_records,
+                                                  dst_depth_keys, dst_radii, row0, send_src,
+                                                  static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(where, e);
+}
+
+int surfel_window_push_grad_rows(int64_t n_rows, const float *grad_rows, int G, const int64_t *seg_count,
+                                 float *const *dst_rows, const int64_t *dst_row0, void *stream)
+{
+    const char *where = "surfel_window_push_grad_rows";
+    if (n_rows < 0 || G < 1 || G > MAX_RANKS) return fail(where, "bad sizes");
+    if (n_rows == 0) return 0;
+    if (!grad_rows || !seg_count || !dst_rows || !dst_row0) return fail(where, "NULL required pointer");
+    long long cnt[MAX_RANKS], row0[MAX_RANKS];
+    for (int s = 0; s < G; s++) {
+        if (seg_count[s] < 0 || dst_row0[s] < 0 || (seg_count[s] > 0 && (!dst_rows[s] || !aligned(dst_rows[s], 16))))
+            return fail(where, "bad destination");
+        cnt[s] = (long long)seg_count[s];
+        row0[s] = (long long)dst_row0[s];
+    }
+    if (!aligned(grad_rows, 16)) return fail(where, "alignment");
+    const cudaError_t e = run_push_grad_rows((long long)n_rows, grad_rows, G, cnt, dst_rows, row0,
+                                             static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda(where, e);
+}
+
 int surfel_window_unpack(int n, const float *rows, float *records, int *radii, uint32_t *depth_keys, void *stream)
 {
     if (n < 0) return fail("surfel_window_unpack", "bad sizes");

@@ -316,6 +316,151 @@ route_scatter_kernel(const int P, const int G, const float *__restrict__ rec, co
     }
 }
 
+static void route_carve(char *temp, int P, int G, uint32_t *&mask, uint32_t *&block_counts, int &nblocks);
+
+// Same routing, exchange fused in: rows are stored STRAIGHT into the receive buffers of their destination ranks over
+// NVLink (symmetric memory), already split into the three arrays the receiver works on -- no send buffer, no
+// all-to-all, no unpack pass.  Destination d receives this rank's rows at [row0[d], row0[d] + send_counts[d]) of its
+// buffers (row0 = rows of lower ranks bound for d, from the all-gathered count matrix), so every receiver ends up with
+// rank-major, index-minor = global index order, exactly like the all-to-all.  A 96-B record is six 16-B stores to
+// consecutive addresses; rows of one CTA land next to each other.
+struct PeerRows {
+    float *rec[MAX_RANKS];
+    uint32_t *keys[MAX_RANKS];
+    int *radii[MAX_RANKS];
+    long long row0[MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(XR_THREADS)
+route_scatter_peers_kernel(const int P, const int G, const float *__restrict__ rec, const int *__restrict__ radii,
+                           const uint32_t *__restrict__ keys, const uint32_t *__restrict__ mask,
+                           const uint32_t *__restrict__ block_base, const int nblocks,
+                           const int *__restrict__ send_counts, const PeerRows dst, uint32_t *__restrict__ send_src)
+{
+    // The CTA's rows for one destination are contiguous there, so they are staged in shared memory in destination
+    // order and written out by consecutive threads on consecutive 16-B words: stores that leave the GPU over NVLink are
+    // not merged by a local L2, a 96-B-strided pattern would travel as 16-B packets.
+    __shared__ float4 s_rec[XR_THREADS * 6];
+    __shared__ uint32_t s_key[XR_THREADS];
+    __shared__ int s_rad[XR_THREADS];
+    __shared__ uint32_t wcnt[MAX_RANKS][XR_THREADS / 32];
+    __shared__ uint32_t seg[MAX_RANKS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t m = g < P ? mask[g] : 0u;
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int d = 0; d < G; d++) { seg[d] = acc; acc += (uint32_t)send_counts[d]; }
+    }
+    uint32_t before[MAX_RANKS];
+#pragma unroll
+    for (int d = 0; d < MAX_RANKS; d++) {
+        before[d] = 0;
+        if (d < G) {
+            const uint32_t b = __ballot_sync(0xffffffffu, (m >> d) & 1u);
+            before[d] = (uint32_t)__popc(b & ((1u << lane) - 1u));
+            if (lane == 0) wcnt[d][warp] = (uint32_t)__popc(b);
+        }
+    }
+    __syncthreads();
+    float4 q[6];
+    uint32_t key = 0;
+    int radius = 0;
+    if (m) {
+        const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)g * REC_FLOATS);
+#pragma unroll
+        for (int i = 0; i < 6; i++) q[i] = src[i];
+        key = keys[g];
+        radius = radii[g];
+    }
+#pragma unroll
+    for (int d = 0; d < MAX_RANKS; d++) {          // unrolled: before[] stays in registers; d < G is CTA-uniform
+        if (d >= G) break;
+        uint32_t total = 0, local = before[d];
+        for (int w = 0; w < XR_THREADS / 32; w++) {
+            const uint32_t c = wcnt[d][w];
+            if (w < warp) local += c;
+            total += c;
+        }
+        if (total == 0) continue;                       // CTA-uniform
+        const uint32_t base = block_base[(size_t)d * nblocks + blockIdx.x];
+        if ((m >> d) & 1u) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) s_rec[local * 6 + i] = q[i];
+            s_key[local] = key;
+            s_rad[local] = radius;
+            send_src[seg[d] + base + local] = (uint32_t)g;
+        }
+        __syncthreads();
+        const size_t row = (size_t)dst.row0[d] + base;
+        float4 *o = reinterpret_cast<float4 *>(dst.rec[d] + row * REC_FLOATS);
+        for (uint32_t w = threadIdx.x; w < total * 6; w += XR_THREADS) o[w] = s_rec[w];
+        for (uint32_t w = threadIdx.x; w < total; w += XR_THREADS) {
+            dst.keys[d][row + w] = s_key[w];
+            dst.radii[d][row + w] = s_rad[w];
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t run_route_scatter_peers(int P, int G, const float *rec, const int *radii, const uint32_t *keys, char *temp,
+                                    const int *send_counts, float *const *dst_rec, uint32_t *const *dst_keys,
+                                    int *const *dst_radii, const long long *dst_row0, uint32_t *send_src,
+                                    cudaStream_t stream)
+{
+    if (P <= 0) return cudaSuccess;
+    uint32_t *mask, *block_counts;
+    int nblocks;
+    route_carve(temp, P, G, mask, block_counts, nblocks);
+    PeerRows dst{};
+    for (int d = 0; d < G; d++) {
+        dst.rec[d] = dst_rec[d]; dst.keys[d] = dst_keys[d]; dst.radii[d] = dst_radii[d]; dst.row0[d] = dst_row0[d];
+    }
+    route_scatter_peers_kernel<<<nblocks, XR_THREADS, 0, stream>>>(P, G, rec, radii, keys, mask, block_counts, nblocks,
+                                                                   send_counts, dst, send_src);
+    return cudaGetLastError();
+}
+
+// Backward counterpart: the gradient rows of the records this rank received go back to their owners.  Rows
+// [seg_start[s], seg_start[s] + seg_count[s]) came from rank s and are stored at row dst_row0[s] + (offset in the
+// segment) of rank s's return buffer = the position of that record in rank s's send order.  One 16-B word per thread,
+// consecutive threads on consecutive words: full-width NVLink stores.
+struct PeerGradRows {
+    float *dst[MAX_RANKS];
+    long long seg_start[MAX_RANKS + 1];
+    long long row0[MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(XR_THREADS)
+push_grad_rows_kernel(const long long n_words, const int G, const float *__restrict__ rows, const PeerGradRows p)
+{
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const long long row = w / 5;
+    const int j = (int)(w - row * 5);
+    int s = 0;
+    while (s + 1 < G && row >= p.seg_start[s + 1]) s++;
+    const float4 v = reinterpret_cast<const float4 *>(rows)[w];
+    reinterpret_cast<float4 *>(p.dst[s] + (size_t)(p.row0[s] + (row - p.seg_start[s])) * GACC_FLOATS)[j] = v;
+}
+
+cudaError_t run_push_grad_rows(long long n_rows, const float *rows, int G, const long long *seg_count,
+                               float *const *dst, const long long *dst_row0, cudaStream_t stream)
+{
+    if (n_rows <= 0) return cudaSuccess;
+    PeerGradRows p{};
+    long long acc = 0;
+    for (int s = 0; s < G; s++) {
+        p.dst[s] = dst[s]; p.row0[s] = dst_row0[s]; p.seg_start[s] = acc;
+        acc += seg_count[s];
+    }
+    for (int s = G; s <= MAX_RANKS; s++) p.seg_start[s] = acc;
+    if (acc != n_rows) return cudaErrorInvalidValue;
+    const long long words = n_rows * 5;
+    push_grad_rows_kernel<<<(unsigned)((words + XR_THREADS - 1) / XR_THREADS), XR_THREADS, 0, stream>>>(words, G, rows, p);
+    return cudaGetLastError();
+}
+
 size_t route_temp_bytes(int P, int G)
 {
     const size_t nblocks = (size_t)(P + XR_THREADS - 1) / XR_THREADS + 1;

@@ -64,6 +64,12 @@ cudaError_t run_route_count(int P, int gx, int gy, int G, const float *rec, cons
                             char *temp, int *send_counts, cudaStream_t stream);
 cudaError_t run_route_scatter(int P, int G, const float *rec, const int *radii, const uint32_t *keys, char *temp,
                               const int *send_counts, float *send_rows, uint32_t *send_src, cudaStream_t stream);
+cudaError_t run_route_scatter_peers(int P, int G, const float *rec, const int *radii, const uint32_t *keys, char *temp,
+                                    const int *send_counts, float *const *dst_rec, uint32_t *const *dst_keys,
+                                    int *const *dst_radii, const long long *dst_row0, uint32_t *send_src,
+                                    cudaStream_t stream);
+cudaError_t run_push_grad_rows(long long n_rows, const float *rows, int G, const long long *seg_count,
+                               float *const *dst, const long long *dst_row0, cudaStream_t stream);
 void launch_unpack_rows(int n, const float *rows, float *rec, uint32_t *keys, int *radii, cudaStream_t stream);
 cudaError_t run_grad_accumulate(int P, long long n_rows, const float *rows, const uint32_t *src, float *gacc,
                                 cudaStream_t stream);

@@ -14,9 +14,12 @@ partitions the SCREEN, and exchanges only *projected* data -- and only with the 
             3. per-destination send counts (a record goes to every rank whose range its tile rect touches:
                1.1-1.3 ranks on average instead of all G), all-gather of the G x G count matrix -- the ONE
                host synchronisation of the forward (sizes of the exchange buffers)
-            4. stable per-destination scatter into 112-B rows (record + depth key + radius), all-to-all
-               over NCCL/NVLink.  Segments arrive in rank order and keep index order inside, i.e. global
-               index order, so the receiver's stable depth sort breaks ties exactly like one GPU does.
+            4. stable per-destination scatter with the exchange fused in: the routing kernel stores every
+               record straight into the receive arrays of its destination ranks over NVLink (symmetric
+               memory, class PeerRows), at row offsets derived from the count matrix; one barrier.
+               Fallback (no peer mappings, CPU/gloo): 112-B rows + NCCL all-to-all + unpack.  Either way
+               segments arrive in rank order and keep index order inside, i.e. global index order, so the
+               receiver's stable depth sort breaks ties exactly like one GPU does.
             5. every rank depth-sorts, bins and blends what it received for its own tiles
                (surfel_window_unpack / _prepare / _render): same lists, order and arithmetic per pixel as
                on one GPU
@@ -27,8 +30,9 @@ partitions the SCREEN, and exchanges only *projected* data -- and only with the 
                exactly one non-zero summand, so the sum is exact
   backward  7. every rank back-propagates its tiles into 80-B gradient rows of the records it received
                                                                      (surfel_window_backward)
-            8. all-to-all of the gradient rows back along the same routes; the owner sums the rows of a
-               Gaussian that went to several ranks (surfel_shard_grad_accumulate)
+            8. the gradient rows go back along the same routes (pushed straight into the owners' symmetric
+               return buffers + barrier, or NCCL all-to-all); the owner sums the rows of a Gaussian that
+               went to several ranks (surfel_shard_grad_accumulate)
             9. every rank turns its accumulator into parameter gradients (surfel_shard_backward)
 
 Contract: the upstream gradients (dL/dcolor, dL/dallmap) must be THE SAME on every rank -- each rank
@@ -150,6 +154,62 @@ class PeerImages:
         return t.view(10, self.H, self.W).clone()
 
 
+ROW_EXCHANGE = _os.environ.get("SURFEL_ROW_EXCHANGE", "auto")       # auto | peers | nccl
+
+
+class PeerRows:
+    """Symmetric receive buffers for the two row exchanges (records forward, gradient rows backward).  With them the
+    routing kernel stores every record straight into its destination ranks' arrays over NVLink, and the backward pushes
+    gradient rows straight back into their owners' buffers: no send buffers, no NCCL all-to-all, no unpack pass; one
+    cross-rank barrier each way.  Capacities grow collectively: every rank knows the whole count matrix after the
+    forward's host synchronisation, so all ranks take the same decision."""
+
+    def __init__(self, device, group):
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.cap_in = self.cap_out = 0
+        self.buf_in = self.hdl_in = self.buf_out = self.hdl_out = None
+
+    @staticmethod
+    def _round(n):
+        n = int(n * 1.25) + 1
+        return -(-n // 65536) * 65536
+
+    def ensure(self, need_in, need_out):
+        import torch.distributed._symmetric_memory as symm
+        if need_in > self.cap_in:
+            self.cap_in = self._round(need_in)
+            self.buf_in = symm.empty((self.cap_in * (REC_FLOATS + 2),), dtype=torch.float32, device=self.device)
+            self.hdl_in = symm.rendezvous(self.buf_in, self.group)
+        if need_out > self.cap_out:
+            self.cap_out = self._round(need_out)
+            self.buf_out = symm.empty((self.cap_out * GREC_FLOATS,), dtype=torch.float32, device=self.device)
+            self.hdl_out = symm.rendezvous(self.buf_out, self.group)
+
+    def in_ptrs(self):
+        """Per rank: addresses of its records / depth keys / radii receive arrays."""
+        base = [int(x) for x in self.hdl_in.buffer_ptrs]
+        c = self.cap_in
+        return base, [b + c * REC_FLOATS * 4 for b in base], [b + c * (REC_FLOATS + 1) * 4 for b in base]
+
+    def out_ptrs(self):
+        return [int(x) for x in self.hdl_out.buffer_ptrs]
+
+    def take_received(self, n):
+        """Barrier (every rank's stores have landed), then private copies of the n received rows: the records are
+        needed again by the backward, by which time a later forward may have refilled the symmetric buffer."""
+        self.hdl_in.barrier(channel=0)
+        c = self.cap_in
+        rec = self.buf_in[:n * REC_FLOATS].view(n, REC_FLOATS).clone()
+        keys = self.buf_in[c * REC_FLOATS:c * REC_FLOATS + n].view(torch.int32).clone()
+        radii = self.buf_in[c * (REC_FLOATS + 1):c * (REC_FLOATS + 1) + n].view(torch.int32).clone()
+        return rec, radii, keys
+
+    def returned(self, n):
+        self.hdl_out.barrier(channel=0)
+        return self.buf_out[:n * GREC_FLOATS].view(n, GREC_FLOATS)
+
+
 # ----------------------------------------------------------------------------------------------------
 # native backend: the CUDA library through its C ABI
 # ----------------------------------------------------------------------------------------------------
@@ -160,6 +220,46 @@ class NativeBackend:
         self.L = _lib.lib()
         self._peer_images = {}
         self.image_exchange = None      # "multicast" | "peers" | "allreduce" once the first frame ran
+        self._peer_rows = {}
+        self.row_exchange = None        # "peers" | "nccl" once the first frame ran
+
+    def peer_rows(self, device, group, need_in, need_out):
+        """Symmetric row buffers with room for this frame, or None -> NCCL all-to-all (SURFEL_ROW_EXCHANGE=nccl, a
+        world of one, or a node without peer mappings)."""
+        if ROW_EXCHANGE == "nccl" or dist.get_world_size(group) == 1:
+            self.row_exchange = "nccl"
+            return None
+        key = device.index
+        if key not in self._peer_rows:
+            try:
+                pr = PeerRows(device, group)
+                pr.ensure(need_in, need_out)
+                self._peer_rows[key] = pr
+            except Exception as exc:   # all ranks fail alike (same node, same software): a collective decision
+                import warnings
+                warnings.warn(f"symmetric-memory row exchange unavailable ({type(exc).__name__}: {exc}); "
+                              f"using NCCL all-to-all")
+                self._peer_rows[key] = None
+        pr = self._peer_rows[key]
+        if pr is not None:
+            pr.ensure(need_in, need_out)
+        self.row_exchange = "peers" if pr is not None else "nccl"
+        return pr
+
+    def route_scatter_peers(self, rec, radii, keys, route_state, send_counts_dev, n_send, world, pr, row0):
+        src = torch.empty((n_send,), dtype=torch.int32, device=rec.device)
+        prec, pkeys, pradii = pr.in_ptrs()
+        A = C.c_void_p * world
+        self._lib.check(self.L.surfel_shard_route_scatter_peers(
+            rec.shape[0], world, self._p(rec), self._p(radii), self._p(keys), C.c_void_p(route_state.data_ptr()),
+            C.c_void_p(send_counts_dev.data_ptr()), A(*prec), A(*pkeys), A(*pradii), (C.c_int64 * world)(*row0),
+            C.c_void_p(src.data_ptr()), self._stream()), "surfel_shard_route_scatter_peers")
+        return src
+
+    def push_grad_rows(self, grows, seg_count, world, pr, row0):
+        self._lib.check(self.L.surfel_window_push_grad_rows(
+            grows.shape[0], self._p(grows), world, (C.c_int64 * world)(*seg_count), (C.c_void_p * world)(*pr.out_ptrs()),
+            (C.c_int64 * world)(*row0), self._stream()), "surfel_window_push_grad_rows")
 
     def peer_images(self, s, device, group):
         """Symmetric image buffers for this resolution, or None -> the caller all-reduces the planes instead
@@ -349,6 +449,7 @@ class _Balancer:
     def __init__(self, world: int, gain: float = 0.7, floor: float = 0.02):
         self.world, self.gain, self.floor = world, gain, floor
         self.shares = [1.0 / world] * world
+        self.last_times_us = None      # the ranks' window times (fwd + bwd, microseconds) of the latest complete measurement
         self.step = 0
         self.records = {}     # step -> {"shares": [...], "ev": [e0, e1, e2, e3]}
 
@@ -384,6 +485,7 @@ class _Balancer:
         rec = self.records.get(step)
         if rec is None or any(t <= 0 for t in times_us):
             return
+        self.last_times_us = [int(t) for t in times_us]
         mean = sum(times_us) / len(times_us)
         new = [s * (mean / t) ** self.gain for s, t in zip(rec["shares"], times_us)]
         tot = sum(new)
@@ -421,16 +523,24 @@ class _ShardedRasterize(torch.autograd.Function):
             out_splits = cmat[:, rank].tolist()
             if balancer is not None:
                 balancer.update(rep_step, gmat[:, world].tolist())
-        with _phase("fwd scatter + all-to-all"):
-            send_rows, send_src = backend.route_scatter(rec, radii, keys, route_state, send_counts, int(sum(in_splits)),
-                                                        world)
-            recv_rows = _all_to_all_rows(send_rows, in_splits, out_splits, group)
-            del send_rows
+        with _phase("fwd record exchange (scatter into peers + barrier | scatter + all-to-all + unpack)"):
+            n_send, n_recv = int(sum(in_splits)), int(sum(out_splits))
+            pr = None
+            if hasattr(backend, "peer_rows"):
+                pr = backend.peer_rows(rec.device, group, int(cmat.sum(0).max()), int(cmat.sum(1).max()))
+            if pr is not None:
+                row0 = [int(cmat[:rank, d].sum()) for d in range(world)]      # rows of lower ranks bound for d
+                send_src = backend.route_scatter_peers(rec, radii, keys, route_state, send_counts, n_send, world, pr, row0)
+                rec_w, radii_w, keys_w = pr.take_received(n_recv)
+            else:
+                send_rows, send_src = backend.route_scatter(rec, radii, keys, route_state, send_counts, n_send, world)
+                recv_rows = _all_to_all_rows(send_rows, in_splits, out_splits, group)
+                del send_rows
+                rec_w, radii_w, keys_w = backend.unpack(recv_rows)
+                del recv_rows
         with _phase("fwd window (sort+bin+blend)"):
             if balancer is not None:
                 balancer.mark(step_id, 0)
-            rec_w, radii_w, keys_w = backend.unpack(recv_rows)
-            del recv_rows
             peers = backend.peer_images(settings, rec.device, group) if hasattr(backend, "peer_images") else None
             if peers is not None:
                 slot = peers.begin()
@@ -450,6 +560,8 @@ class _ShardedRasterize(torch.autograd.Function):
                          shares=list(balancer.shares) if balancer is not None else None)
         ctx.settings, ctx.backend, ctx.group, ctx.state = settings, backend, group, state
         ctx.splits = (in_splits, out_splits)
+        ctx.peer_rows = pr
+        ctx.back_row0 = [int(cmat[src, :rank].sum()) for src in range(world)] if pr is not None else None
         ctx.check_replicated = check_replicated
         ctx.balancer, ctx.step_id = balancer, step_id
         ctx.num_rendered = R
@@ -475,8 +587,13 @@ class _ShardedRasterize(torch.autograd.Function):
             grows = backend.window_backward(s, rec_w, ctx.state, g_color.contiguous(), g_others.contiguous())
             if ctx.balancer is not None:
                 ctx.balancer.mark(ctx.step_id, 3)
-        with _phase("bwd all-to-all"):
-            back = _all_to_all_rows(grows, out_splits, in_splits, group)
+        with _phase("bwd gradient rows (push into peers + barrier | all-to-all)"):
+            if ctx.peer_rows is not None:
+                # my rows for owner `src` start where the rows of lower-ranked receivers end in src's send order
+                backend.push_grad_rows(grows, out_splits, len(out_splits), ctx.peer_rows, ctx.back_row0)
+                back = ctx.peer_rows.returned(int(sum(in_splits)))
+            else:
+                back = _all_to_all_rows(grows, out_splits, in_splits, group)
         with _phase("bwd per-Gaussian"):
             gacc = backend.grad_accumulate(means3D.shape[0], back, send_src)
             g = backend.shard_backward(s, means3D, shs, scales, rotations, radii, rec, clamped, gacc, None)

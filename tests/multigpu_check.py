@@ -69,7 +69,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print(f"[rank {rank}/{world}] shard [{lo},{hi}) R_window={color.grad_fn.num_rendered} image exchange: "
-          f"{rast.backend.image_exchange} " + " ".join(msgs), flush=True)
+          f"{rast.backend.image_exchange}, row exchange: {rast.backend.row_exchange} " + " ".join(msgs), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if int(flag.item()) != 1:

@@ -16,7 +16,33 @@ from streetunveiler_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 
-def _virtual_sharded(scene, cam, bounds, grads, bg):
+class _LocalPeerRows:
+    """PeerRows look-alike whose "peers" are plain tensors on this GPU (one receive / return buffer per virtual rank)."""
+
+    def __init__(self, G, cap_in, cap_out, dev):
+        from streetunveiler_b200.sharded import REC_FLOATS, GREC_FLOATS
+        self.cap_in, self.cap_out, self.RF, self.GF = cap_in, cap_out, REC_FLOATS, GREC_FLOATS
+        self.bufs_in = [torch.full((cap_in * (REC_FLOATS + 2),), float("nan"), device=dev) for _ in range(G)]
+        self.bufs_out = [torch.full((cap_out * GREC_FLOATS,), float("nan"), device=dev) for _ in range(G)]
+
+    def in_ptrs(self):
+        base = [b.data_ptr() for b in self.bufs_in]
+        c = self.cap_in
+        return base, [b + c * self.RF * 4 for b in base], [b + c * (self.RF + 1) * 4 for b in base]
+
+    def out_ptrs(self):
+        return [b.data_ptr() for b in self.bufs_out]
+
+    def received(self, d, n):
+        c, b = self.cap_in, self.bufs_in[d]
+        return (b[:n * self.RF].view(n, self.RF).clone(), b[c * (self.RF + 1):c * (self.RF + 1) + n].view(torch.int32).clone(),
+                b[c * self.RF:c * self.RF + n].view(torch.int32).clone())
+
+    def returned(self, r, n):
+        return self.bufs_out[r][:n * self.GF].view(n, self.GF)
+
+
+def _virtual_sharded(scene, cam, bounds, grads, bg, use_peers=False):
     from streetunveiler_b200.sharded import NativeBackend
     be = NativeBackend()
     dev = torch.device("cuda")
@@ -30,8 +56,15 @@ def _virtual_sharded(scene, cam, bounds, grads, bg):
     cuts_h, wr_h = cuts.cpu().tolist(), window_R.cpu().tolist()
     routes = [be.route_count(s, rec, radii, cuts, G) for radii, rec, keys, clamped in pre]
     cmat = torch.stack([c for _, c in routes]).cpu()                         # [src, dst]
-    sends = [be.route_scatter(rec, radii, keys, routes[r][0], routes[r][1], int(cmat[r].sum()), G)
-             for r, (radii, rec, keys, clamped) in enumerate(pre)]
+    pr = None
+    if use_peers:   # the fused exchange: every rank's routing kernel stores into every rank's receive arrays
+        pr = _LocalPeerRows(G, int(cmat.sum(0).max()) + 64, int(cmat.sum(1).max()) + 64, dev)
+        sends = [(None, be.route_scatter_peers(rec, radii, keys, routes[r][0], routes[r][1], int(cmat[r].sum()), G, pr,
+                                               [int(cmat[:r, d].sum()) for d in range(G)]))
+                 for r, (radii, rec, keys, clamped) in enumerate(pre)]
+    else:
+        sends = [be.route_scatter(rec, radii, keys, routes[r][0], routes[r][1], int(cmat[r].sum()), G)
+                 for r, (radii, rec, keys, clamped) in enumerate(pre)]
 
     def seg(r, d):   # rows of rank r's send buffer bound for rank d
         a = int(cmat[r, :d].sum())
@@ -39,8 +72,11 @@ def _virtual_sharded(scene, cam, bounds, grads, bg):
 
     planes, states, recs_w = torch.zeros(10, cam.height, cam.width, device=dev), [], []
     for d in range(G):
-        rows = torch.cat([sends[r][0][seg(r, d)] for r in range(G)], 0)      # all-to-all: segments in source-rank order
-        rec_w, radii_w, keys_w = be.unpack(rows)
+        if use_peers:
+            rec_w, radii_w, keys_w = pr.received(d, int(cmat[:, d].sum()))
+        else:
+            rows = torch.cat([sends[r][0][seg(r, d)] for r in range(G)], 0)  # all-to-all: segments in source-rank order
+            rec_w, radii_w, keys_w = be.unpack(rows)
         pl, st = be.window_forward(s, rec_w, radii_w, keys_w, cuts_h[d], cuts_h[d + 1], int(wr_h[d]))
         planes += pl                                                          # image all-reduce
         states.append(st)
@@ -49,12 +85,19 @@ def _virtual_sharded(scene, cam, bounds, grads, bg):
     grows = [be.window_backward(s, recs_w[d], states[d], gc, ga) for d in range(G)]
     out = {"color": planes[:3].cpu().numpy(), "allmap": planes[3:].cpu().numpy(), "cuts": cuts_h, "window_R": wr_h,
            "cmat": cmat, "radii": torch.cat([p[0] for p in pre]).cpu().numpy()}
+    if use_peers:   # every rank pushes the gradient rows of what it received back into the owners' return buffers
+        for d in range(G):
+            be.push_grad_rows(grows[d], [int(cmat[r, d]) for r in range(G)], G, pr,
+                              [int(cmat[r, :d].sum()) for r in range(G)])
     g_all = {}
     for r, (radii, rec, keys, clamped) in enumerate(pre):
         def rseg(d):   # rows of rank d's receive buffer that came from rank r
             a = int(cmat[:r, d].sum())
             return slice(a, a + int(cmat[r, d]))
         back = torch.cat([grows[d][rseg(d)] for d in range(G)], 0)            # all-to-all back
+        if use_peers:
+            assert torch.equal(pr.returned(r, back.shape[0]), back)           # the push kernel is that all-to-all
+            back = pr.returned(r, back.shape[0])
         gacc = be.grad_accumulate(rec.shape[0], back, sends[r][1])
         p = sh[r]
         g = be.shard_backward(s, p["means3D"], p["shs"], p["scales"], p["rotations"], radii, rec, clamped, gacc, None)
@@ -65,8 +108,10 @@ def _virtual_sharded(scene, cam, bounds, grads, bg):
     return out
 
 
-@pytest.mark.parametrize("G,P,mode", [(2, 120_000, "all"), (3, 120_000, "color_alpha"), (8, 400_000, "all")])
-def test_virtual_ranks_equal_single_gpu(G, P, mode):
+@pytest.mark.parametrize("G,P,mode,use_peers", [(2, 120_000, "all", False), (3, 120_000, "color_alpha", False),
+                                                (8, 400_000, "all", False), (3, 120_000, "all", True),
+                                                (8, 400_000, "color_alpha", True)])
+def test_virtual_ranks_equal_single_gpu(G, P, mode, use_peers):
     cam = syn.make_camera(960, 640, 1027.5, 1027.5)
     scene = syn.street_scene(P, 4, 3)
     grads = syn.upstream_grads(cam.width, cam.height, mode, seed=11)
@@ -75,7 +120,7 @@ def test_virtual_ranks_equal_single_gpu(G, P, mode):
     bounds = [0] + [int(P * (r + 1) / G) - (7 * (r + 1) if r + 1 < G else 0) for r in range(G)]
     if G == 3:
         bounds[2] = bounds[1]
-    v = _virtual_sharded(scene, cam, bounds, grads, bg)
+    v = _virtual_sharded(scene, cam, bounds, grads, bg, use_peers)
     ref = hz.run_ours(scene, cam, bg=bg, grads=grads)
     # the image all-reduce adds each rank's planes to zeros: exact; the background term T * bg is part of every tile
     assert np.array_equal(v["color"], ref["color"]) and np.array_equal(v["allmap"], ref["allmap"])
