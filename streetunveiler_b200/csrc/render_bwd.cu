@@ -206,6 +206,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                                                             dL_dnormal2D[0] != 0.f || dL_dnormal2D[1] != 0.f ||
                                                             dL_dnormal2D[2] != 0.f);
 
+    const uint32_t rec_base = smem_addr(&ring.rec[0][0]);
     int stage = 0;
     uint32_t phase = 0;
     for (int cb = 0; cb < nchunks; cb++) {
@@ -217,6 +218,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
         // `full` would let this warp lap the ring and double-count in a phase other warps still read.
         mbar_wait(&ring.full[stage], phase);
         const float *sb = ring.rec[stage];
+        const uint32_t sb_addr = rec_base + (uint32_t)stage * (CHUNK * REC_BYTES);
         for (int c = 0; chunk_live && c < n; c += 32) {
             const int pos_first = pos0 - c;
             const int pos_min = pos_first - (min(32, n - c) - 1);
@@ -244,8 +246,8 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                 bool valid = false;
 
                 if (contributor < last_contributor) {
-                    const float4 *r4 = reinterpret_cast<const float4 *>(sb + jj * REC_FLOATS);
-                    const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
+                    const uint32_t ra = sb_addr + (uint32_t)jj * REC_BYTES;
+                    const float4 q0 = lds128(ra), q1 = lds128(ra + 16), q2 = lds128(ra + 32);
                     const float3 Tu = make_float3(q0.x, q0.y, q0.z);
                     const float3 Tv = make_float3(q0.w, q1.x, q1.y);
                     const float3 Tw = make_float3(q1.z, q1.w, q2.x);
@@ -266,17 +268,24 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                             const float alpha = fminf(0.99f, opa * G);
                             if (!(alpha < ALPHA_MIN)) {
                                 valid = true;
-                                const float4 q3 = r4[3];
+                                const float4 q3 = lds128(ra + 48);
                                 const float normal[3] = {q3.x, q3.y, q3.z};
 
                                 // The reference keeps (last_alpha, last_color, ...) and folds them into the
                                 // suffix accumulators at the NEXT contributor (backward.cu:329,365-374); folding
                                 // them right after use is the same arithmetic on the same operands, with 8 fewer
                                 // live registers.  Divisions that only feed gradients (not the alpha / skip
-                                // decisions above) use the approximate reciprocal: <= 2 ulp, far inside the
-                                // 1e-4 tolerance and below the reference's own atomic-order noise.
+                                // decisions above) use the approximate reciprocal (rcp.approx.ftz, <= 1 ulp; the
+                                // reference divides IEEE-exactly): far inside the 1e-4 tolerance and below the
+                                // reference's own atomic-order noise.  Stated in include/surfel_rasterizer.h.
                                 const float one_m_alpha = 1.f - alpha;
-                                T = T / one_m_alpha;
+                                // 1 / (1 - alpha) is needed twice (T recovery, background term); one approximate
+                                // reciprocal (<= 1 ulp) serves both.  T only feeds gradients here (the forward's T is
+                                // not recomputed), and the product T * inv carries ~1.5 ulp per step instead of the
+                                // 0.5 ulp of an IEEE division: a random walk of ~1e-6 over a pixel's list, below the
+                                // reference's own atomic-order noise (the live test prints the margin to 1e-4).
+                                const float inv_oma = fast_rcp(one_m_alpha);
+                                T = T * inv_oma;
                                 const float w = alpha * T;
                                 float dL_dalpha = 0.0f;
                                 if constexpr (CLASSES) {
@@ -287,7 +296,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                                     dL_dalpha = g_label - accum_rec[0];
                                     accum_rec[0] = alpha * g_label + one_m_alpha * accum_rec[0];
                                 } else {
-                                    const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
+                                    const float2 q4 = lds64(ra + 64);
                                     const float col[3] = {q3.w, q4.x, q4.y};
 #pragma unroll
                                     for (int ch = 0; ch < 3; ch++) {
@@ -323,7 +332,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                                     accum_alpha_rec = alpha + one_m_alpha * accum_alpha_rec;
                                 }
                                 dL_dalpha *= T;
-                                dL_dalpha += (-T_final * fast_rcp(one_m_alpha)) * bg_dot_dpixel;
+                                dL_dalpha += (-T_final * inv_oma) * bg_dot_dpixel;
 
                                 const float dL_dG = opa * dL_dalpha;
 

@@ -161,6 +161,22 @@ __device__ __forceinline__ bool ring_wait_or_quit(TileRing<NSTAGE> &r, const int
     }
 }
 
+// 128-/64-bit loads from a 32-bit shared-space address.  The record loads of the blend loops use these instead of
+// generic pointers: with generic addressing the compiler rebuilt the shared-window base (S2R SR_CgaCtaId + LEA + two
+// IMADs) for every evaluated (warp, instance) pair.
+__device__ __forceinline__ float4 lds128(const uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(const uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
 // Conservative test: can any pixel of the 8x4 block at (bx0, by0) reach alpha >= 1/255 for the splat
 // whose record is at `rp`?  See preprocess.cu cull_footprint: 8-px bounding box first, then the low-pass
 // disc and (when present) the ellipse against the block inflated by half a pixel, with a threshold
@@ -184,7 +200,12 @@ __device__ __forceinline__ bool block_may_contribute(const float *rp, const int 
     const float ex = rp[19], ey = m.x, m00 = m.y, m01 = m.z, m11 = m.w;
     const float X0 = rx0 - ex, X1 = rx1 - ex, Y0 = ry0 - ey, Y1 = ry1 - ey;
     if (X0 <= 0.f && X1 >= 0.f && Y0 <= 0.f && Y1 >= 0.f) return true;
-    const float ky = -m01 * __frcp_rn(m11), kx = -m01 * __frcp_rn(m00);
+    // (approximate reciprocals: the clamped minimiser moves by ~1 ulp, g changes in second order -- far inside the
+    // 0.02 + evaluation-error margin of the threshold below; the IEEE version cost two slow-path-checked calls per test)
+    float r11, r00;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r11) : "f"(m11));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r00) : "f"(m00));
+    const float ky = -m01 * r11, kx = -m01 * r00;
     float gmin;
     {
         const float Ya = fminf(fmaxf(ky * X0, Y0), Y1), Yb = fminf(fmaxf(ky * X1, Y0), Y1);
