@@ -206,7 +206,6 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                                                             dL_dnormal2D[0] != 0.f || dL_dnormal2D[1] != 0.f ||
                                                             dL_dnormal2D[2] != 0.f);
 
-    const uint32_t rec_base = smem_addr(&ring.rec[0][0]);
     int stage = 0;
     uint32_t phase = 0;
     for (int cb = 0; cb < nchunks; cb++) {
@@ -218,7 +217,6 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
         // `full` would let this warp lap the ring and double-count in a phase other warps still read.
         mbar_wait(&ring.full[stage], phase);
         const float *sb = ring.rec[stage];
-        const uint32_t sb_addr = rec_base + (uint32_t)stage * (CHUNK * REC_BYTES);
         for (int c = 0; chunk_live && c < n; c += 32) {
             const int pos_first = pos0 - c;
             const int pos_min = pos_first - (min(32, n - c) - 1);
@@ -246,8 +244,8 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                 bool valid = false;
 
                 if (contributor < last_contributor) {
-                    const uint32_t ra = sb_addr + (uint32_t)jj * REC_BYTES;
-                    const float4 q0 = lds128(ra), q1 = lds128(ra + 16), q2 = lds128(ra + 32);
+                    const float4 *r4 = reinterpret_cast<const float4 *>(sb + jj * REC_FLOATS);
+                    const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
                     const float3 Tu = make_float3(q0.x, q0.y, q0.z);
                     const float3 Tv = make_float3(q0.w, q1.x, q1.y);
                     const float3 Tw = make_float3(q1.z, q1.w, q2.x);
@@ -268,7 +266,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                             const float alpha = fminf(0.99f, opa * G);
                             if (!(alpha < ALPHA_MIN)) {
                                 valid = true;
-                                const float4 q3 = lds128(ra + 48);
+                                const float4 q3 = r4[3];
                                 const float normal[3] = {q3.x, q3.y, q3.z};
 
                                 // The reference keeps (last_alpha, last_color, ...) and folds them into the
@@ -296,7 +294,7 @@ render_bwd_kernel(const int *__restrict__ aux_flag, const int n_classes,
                                     dL_dalpha = g_label - accum_rec[0];
                                     accum_rec[0] = alpha * g_label + one_m_alpha * accum_rec[0];
                                 } else {
-                                    const float2 q4 = lds64(ra + 64);
+                                    const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
                                     const float col[3] = {q3.w, q4.x, q4.y};
 #pragma unroll
                                     for (int ch = 0; ch < 3; ch++) {

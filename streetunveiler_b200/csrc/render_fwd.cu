@@ -98,7 +98,6 @@ render_fwd_kernel(const PeerPlanes peers, const int n_classes,
     bool warp_done = __all_sync(0xffffffffu, done);
     if (warp_done && lane == 0) atomicAdd(const_cast<int *>(&ring.done_warps), 1);
 
-    const uint32_t rec_base = smem_addr(&ring.rec[0][0]);
     int stage = 0;
     uint32_t phase = 0;
     for (int c = 0; c < nchunks; c++) {
@@ -106,7 +105,6 @@ render_fwd_kernel(const PeerPlanes peers, const int n_classes,
             mbar_wait(&ring.full[stage], phase);
             const int n = min(CHUNK, total - c * CHUNK);
             const float *sb = ring.rec[stage];
-            const uint32_t sb_addr = rec_base + (uint32_t)stage * (CHUNK * REC_BYTES);
 #pragma unroll 1
             for (int h = 0; h < n; h += 32) {
                 uint32_t mask;
@@ -121,8 +119,11 @@ render_fwd_kernel(const PeerPlanes peers, const int n_classes,
                     const int jj = h + __ffs(mask) - 1;
                     mask &= mask - 1;
                     if (!done) {
-                        const uint32_t ra = sb_addr + (uint32_t)jj * REC_BYTES;
-                        const float4 q0 = lds128(ra), q1 = lds128(ra + 16), q2 = lds128(ra + 32);
+                        // (plain generic loads on purpose: with explicit ld.shared asm the compiler contracted the
+                        // intersection arithmetic into different FMAs and the forward stopped being bit-identical
+                        // to the reference -- measured 1.7e-7, which the caller's depth-difference normals amplify)
+                        const float4 *r4 = reinterpret_cast<const float4 *>(sb + jj * REC_FLOATS);
+                        const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
                         const float3 Tu = make_float3(q0.x, q0.y, q0.z);
                         const float3 Tv = make_float3(q0.w, q1.x, q1.y);
                         const float3 Tw = make_float3(q1.z, q1.w, q2.x);
@@ -145,7 +146,7 @@ render_fwd_kernel(const PeerPlanes peers, const int n_classes,
                                     if (test_T < T_EPS) {
                                         done = true;
                                     } else {
-                                        const float4 q3 = lds128(ra + 48);
+                                        const float4 q3 = r4[3];
                                         const uint32_t contributor = (uint32_t)(c * CHUNK + jj + 1);
                                         const float w = alpha * T;
                                         if constexpr (CLASSES) {
@@ -153,7 +154,7 @@ render_fwd_kernel(const PeerPlanes peers, const int n_classes,
 #pragma unroll
                                             for (int k = 0; k < NC; k++) C[k] += (label == k) ? w : 0.f;
                                         } else {
-                                            const float2 q4 = lds64(ra + 64);
+                                            const float2 q4 = *reinterpret_cast<const float2 *>(r4 + 4);
                                             const float A = 1 - T;
                                             const float m = FAR_N / (FAR_N - NEAR_N) * (1 - NEAR_N / depth);
                                             distortion += (m * m * A + M2 - 2 * m * M1) * w;

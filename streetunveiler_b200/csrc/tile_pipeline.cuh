@@ -161,22 +161,6 @@ __device__ __forceinline__ bool ring_wait_or_quit(TileRing<NSTAGE> &r, const int
     }
 }
 
-// 128-/64-bit loads from a 32-bit shared-space address.  The record loads of the blend loops use these instead of
-// generic pointers: with generic addressing the compiler rebuilt the shared-window base (S2R SR_CgaCtaId + LEA + two
-// IMADs) for every evaluated (warp, instance) pair.
-__device__ __forceinline__ float4 lds128(const uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float2 lds64(const uint32_t addr)
-{
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-
 // Conservative test: can any pixel of the 8x4 block at (bx0, by0) reach alpha >= 1/255 for the splat
 // whose record is at `rp`?  See preprocess.cu cull_footprint: 8-px bounding box first, then the low-pass
 // disc and (when present) the ellipse against the block inflated by half a pixel, with a threshold
