@@ -670,6 +670,23 @@ def run_ours(args):
         line["config5_strong"] = strong
     if phases:
         line["shard_phase_ms"] = phases
+    if sharded is not None:
+        from streetunveiler_b200 import sharded as _shm
+        info = _shm.LAST_INFO
+        if info.get("send"):
+            snd, rcv = info["send"], info["recv"]
+            own = world and rank
+            out_rows = sum(snd) - snd[rank]
+            back_rows = sum(rcv) - rcv[rank]
+            HW_ = wl.cam.width * wl.cam.height
+            owned = info["cuts"][rank + 1] - info["cuts"][rank]
+            line["shard_exchange_rank0"] = {
+                "records_sent_rows": int(sum(snd)), "records_leaving_gpu_rows": int(out_rows),
+                "records_leaving_gpu_bytes": int(out_rows * 104), "gradient_rows_leaving_gpu_bytes": int(back_rows * 80),
+                "image_bytes_stored_by_this_rank": int(owned * 256 * 40 * (1 if sharded.backend.image_exchange == "multicast" else world)),
+                "rows_per_visible_gaussian": round(sum(snd) / max(1, P_vis), 3), "tile_range": [info["cuts"][rank], info["cuts"][rank + 1]],
+                "note": "last step of the run on rank 0 (the strong-scaling scene when that leg ran); NVLink payload only, "
+                        "records travel as 96 B + 4 B key + 4 B radius, gradient rows as 80 B, image pixels as 40 B"}
     if sharded is not None and sharded.balancer is not None and sharded.balancer.last_times_us:
         t = sharded.balancer.last_times_us
         line["shard_balance"] = {"window_fwd_bwd_us_per_rank": t, "imbalance_max_over_mean": round(max(t) / (sum(t) / len(t)), 3),
