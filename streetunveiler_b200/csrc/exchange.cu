@@ -16,6 +16,7 @@
 //   route_scatter  packed 112-B rows (record + depth key + radius) into per-destination segments of the send buffer
 //   unpack         received rows -> 96-B records (16-B aligned, one cp.async.bulk each), keys, radii
 //   grad_accumulate  returned 80-B gradient rows summed into the owner's per-Gaussian accumulator
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -340,7 +341,7 @@ route_scatter_peers_kernel(const int P, const int G, const float *__restrict__ r
     // The CTA's rows for one destination are contiguous there, so they are staged in shared memory in destination
     // order and written out by consecutive threads on consecutive 16-B words: stores that leave the GPU over NVLink are
     // not merged by a local L2, a 96-B-strided pattern would travel as 16-B packets.
-    __shared__ float4 s_rec[XR_THREADS * 6];
+    __shared__ __align__(128) float4 s_rec[XR_THREADS * 6];
     __shared__ uint32_t s_key[XR_THREADS];
     __shared__ int s_rad[XR_THREADS];
     __shared__ uint32_t wcnt[MAX_RANKS][XR_THREADS / 32];
@@ -393,14 +394,24 @@ route_scatter_peers_kernel(const int P, const int G, const float *__restrict__ r
         }
         __syncthreads();
         const size_t row = (size_t)dst.row0[d] + base;
-        float4 *o = reinterpret_cast<float4 *>(dst.rec[d] + row * REC_FLOATS);
-        for (uint32_t w = threadIdx.x; w < total * 6; w += XR_THREADS) o[w] = s_rec[w];
+        float *o = dst.rec[d] + row * REC_FLOATS;
+        if (threadIdx.x == 0) {
+            // one bulk store (TMA engine, shared -> global) moves the CTA's whole block for this destination: a few KB
+            // per request on the NVLink instead of 16-B stores
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o), "r"(smem_addr(s_rec)),
+                         "r"(total * (uint32_t)REC_BYTES)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         for (uint32_t w = threadIdx.x; w < total; w += XR_THREADS) {
             dst.keys[d][row + w] = s_key[w];
             dst.radii[d][row + w] = s_rad[w];
         }
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer reusable
         __syncthreads();
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores performed before exit
 }
 
 cudaError_t run_route_scatter_peers(int P, int G, const float *rec, const int *radii, const uint32_t *keys, char *temp,

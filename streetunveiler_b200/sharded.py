@@ -172,7 +172,9 @@ class PeerRows:
 
     @staticmethod
     def _round(n):
-        n = int(n * 1.25) + 1
+        # generous: re-allocating is a collective rendezvous (tens of ms), and the balancer may double a rank's share
+        # of the screen after the first frames; HBM is not the constraint (2M rows = 208 MB)
+        n = int(n * 2.5) + 1
         return -(-n // 65536) * 65536
 
     def ensure(self, need_in, need_out):
