@@ -213,11 +213,13 @@ SURFEL_API size_t surfel_shard_partition_bytes(int width, int height);
 SURFEL_API int surfel_shard_partition(int width, int height, int G, const uint32_t *hist, int cost_base,
                                       const float *shares, char *temp, int *cuts, int64_t *window_num_rendered,
                                       void *stream);
-/* temp: surfel_shard_route_bytes(P, G), shared by the two calls.  send_counts: DEVICE int32[G].
+/* temp: surfel_shard_route_bytes(P, G), shared by the two calls.  send_counts: DEVICE int32[G + 1]; word G receives
+ * `extra`, a caller-defined value that travels with the counts through the all-gather (the host side puts the
+ * rank's last measured blend time there).
  * send_rows: [sum(send_counts), 28] fp32, segment d = rows for rank d; send_src[row] = local Gaussian index. */
 SURFEL_API size_t surfel_shard_route_bytes(int P, int G);
 SURFEL_API int surfel_shard_route_count(int P, int width, int height, int G, const float *records, const int *radii,
-                                        const int *cuts, char *temp, int *send_counts, void *stream);
+                                        const int *cuts, char *temp, int *send_counts, int extra, void *stream);
 SURFEL_API int surfel_shard_route_scatter(int P, int G, const float *records, const int *radii,
                                           const uint32_t *depth_keys, char *temp, const int *send_counts,
                                           float *send_rows, uint32_t *send_src, void *stream);

@@ -39,7 +39,7 @@ SIGNATURES = {
     "surfel_shard_partition_bytes": (C.c_size_t, [_i, _i]),
     "surfel_shard_partition": (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "surfel_shard_route_bytes": (C.c_size_t, [_i, _i]),
-    "surfel_shard_route_count": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "surfel_shard_route_count": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "surfel_shard_route_scatter": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_shard_route_scatter_peers": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "surfel_window_push_grad_rows": (_i, [_i64, _vp, _i, _vp, _vp, _vp, _vp]),

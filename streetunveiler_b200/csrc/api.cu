@@ -764,13 +764,13 @@ size_t surfel_shard_route_bytes(int P, int G)
 }
 
 int surfel_shard_route_count(int P, int width, int height, int G, const float *records, const int *radii,
-                             const int *cuts, char *temp, int *send_counts, void *stream)
+                             const int *cuts, char *temp, int *send_counts, int extra, void *stream)
 {
     if (P < 0 || width <= 0 || height <= 0 || G < 1 || G > MAX_RANKS) return fail("surfel_shard_route_count", "bad sizes");
     if (!cuts || !send_counts || (P > 0 && (!records || !radii || !temp)))
         return fail("surfel_shard_route_count", "NULL required pointer");
     const int gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
-    const cudaError_t e = run_route_count(P, gx, gy, G, records, radii, cuts, temp, send_counts,
+    const cudaError_t e = run_route_count(P, gx, gy, G, records, radii, cuts, temp, send_counts, extra,
                                           static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda("surfel_shard_route_count", e);
 }

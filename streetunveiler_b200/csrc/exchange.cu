@@ -239,8 +239,10 @@ route_count_kernel(const int P, const int gx, const int gy, const int G, const f
 
 // Row d (one CTA): exclusive scan of block_counts[d][*] in place; row total -> send_counts[d].
 __global__ void __launch_bounds__(256)
-route_scan_kernel(const int nblocks, uint32_t *__restrict__ block_counts, int *__restrict__ send_counts)
+route_scan_kernel(const int nblocks, uint32_t *__restrict__ block_counts, int *__restrict__ send_counts, const int G,
+                  const int extra)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) send_counts[G] = extra;   // a caller-defined word that travels with the counts
     __shared__ uint32_t warp_sum[8];
     __shared__ uint32_t carry_s;
     uint32_t *row = block_counts + (size_t)blockIdx.x * nblocks;
@@ -486,15 +488,24 @@ static void route_carve(char *temp, int P, int G, uint32_t *&mask, uint32_t *&bl
     block_counts = carve<uint32_t>(p, (size_t)(nblocks + 1) * G);
 }
 
-cudaError_t run_route_count(int P, int gx, int gy, int G, const float *rec, const int *radii, const int *cuts,
-                            char *temp, int *send_counts, cudaStream_t stream)
+__global__ void route_empty_kernel(int *send_counts, const int G, const int extra)
 {
-    if (P <= 0) return cudaMemsetAsync(send_counts, 0, sizeof(int) * G, stream);
+    for (int d = threadIdx.x; d < G; d += blockDim.x) send_counts[d] = 0;
+    if (threadIdx.x == 0) send_counts[G] = extra;
+}
+
+cudaError_t run_route_count(int P, int gx, int gy, int G, const float *rec, const int *radii, const int *cuts,
+                            char *temp, int *send_counts, int extra, cudaStream_t stream)
+{
+    if (P <= 0) {
+        route_empty_kernel<<<1, 32, 0, stream>>>(send_counts, G, extra);
+        return cudaGetLastError();
+    }
     uint32_t *mask, *block_counts;
     int nblocks;
     route_carve(temp, P, G, mask, block_counts, nblocks);
     route_count_kernel<<<nblocks, XR_THREADS, 0, stream>>>(P, gx, gy, G, rec, radii, cuts, mask, block_counts, nblocks);
-    route_scan_kernel<<<G, 256, 0, stream>>>(nblocks, block_counts, send_counts);
+    route_scan_kernel<<<G, 256, 0, stream>>>(nblocks, block_counts, send_counts, G, extra);
     return cudaGetLastError();
 }
 

@@ -61,7 +61,7 @@ void launch_partition(int ntiles, int G, const uint32_t *hist, uint32_t cost_bas
                       char *temp, int *cuts, long long *window_R, cudaStream_t stream);
 size_t route_temp_bytes(int P, int G);
 cudaError_t run_route_count(int P, int gx, int gy, int G, const float *rec, const int *radii, const int *cuts,
-                            char *temp, int *send_counts, cudaStream_t stream);
+                            char *temp, int *send_counts, int extra, cudaStream_t stream);
 cudaError_t run_route_scatter(int P, int G, const float *rec, const int *radii, const uint32_t *keys, char *temp,
                               const int *send_counts, float *send_rows, uint32_t *send_src, cudaStream_t stream);
 cudaError_t run_route_scatter_peers(int P, int G, const float *rec, const int *radii, const uint32_t *keys, char *temp,

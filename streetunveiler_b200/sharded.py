@@ -345,15 +345,16 @@ class NativeBackend:
                                                       C.c_void_p(wr.data_ptr()), self._stream()), "surfel_shard_partition")
         return cuts, wr
 
-    def route_count(self, s, rec, radii, cuts, world):
+    def route_count(self, s, rec, radii, cuts, world, extra=0):
+        """-> (routing state, int32[G + 1] on the device: send counts per destination, then `extra`)."""
         P, dev = rec.shape[0], rec.device
         tmp = torch.empty((self._lib.size(self.L.surfel_shard_route_bytes(P, world), "surfel_shard_route_bytes"),),
                           dtype=torch.uint8, device=dev)
-        counts = torch.empty((world,), dtype=torch.int32, device=dev)
+        counts = torch.empty((world + 1,), dtype=torch.int32, device=dev)
         self._lib.check(self.L.surfel_shard_route_count(P, s.image_width, s.image_height, world, self._p(rec),
                                                         self._p(radii), C.c_void_p(cuts.data_ptr()),
                                                         C.c_void_p(tmp.data_ptr()), C.c_void_p(counts.data_ptr()),
-                                                        self._stream()), "surfel_shard_route_count")
+                                                        int(extra), self._stream()), "surfel_shard_route_count")
         return tmp, counts
 
     def route_scatter(self, rec, radii, keys, route_state, send_counts_dev, n_send, world):
@@ -512,10 +513,9 @@ class _ShardedRasterize(torch.autograd.Function):
             dist.all_reduce(hist, group=group)
             cuts, window_R = backend.partition(settings, hist, world, balancer.shares if balancer is not None else None)
         with _phase("fwd route counts + host sync"):
-            route_state, send_counts = backend.route_count(settings, rec, radii, cuts, world)
             rep_step, rep_us = balancer.report() if balancer is not None else (0, 0)
-            extra = torch.tensor([rep_us], dtype=send_counts.dtype).to(send_counts.device, non_blocking=True)
-            gathered = _all_gather_rows(torch.cat([send_counts, extra]), group).view(world, world + 1)
+            route_state, send_counts = backend.route_count(settings, rec, radii, cuts, world, min(rep_us, 2 ** 31 - 1))
+            gathered = _all_gather_rows(send_counts, group).view(world, world + 1)
             host = torch.cat([gathered.flatten().to(torch.int64), cuts.to(torch.int64), window_R.to(torch.int64)]).cpu()
             gmat = host[:world * (world + 1)].view(world, world + 1)
             cmat = gmat[:, :world]

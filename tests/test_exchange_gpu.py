@@ -55,7 +55,7 @@ def _virtual_sharded(scene, cam, bounds, grads, bg, use_peers=False):
     cuts, window_R = be.partition(s, hist, G)
     cuts_h, wr_h = cuts.cpu().tolist(), window_R.cpu().tolist()
     routes = [be.route_count(s, rec, radii, cuts, G) for radii, rec, keys, clamped in pre]
-    cmat = torch.stack([c for _, c in routes]).cpu()                         # [src, dst]
+    cmat = torch.stack([c[:G] for _, c in routes]).cpu()                     # [src, dst]
     pr = None
     if use_peers:   # the fused exchange: every rank's routing kernel stores into every rank's receive arrays
         pr = _LocalPeerRows(G, int(cmat.sum(0).max()) + 64, int(cmat.sum(1).max()) + 64, dev)

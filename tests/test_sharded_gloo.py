@@ -65,10 +65,10 @@ class ToyBackend:
         window_R = torch.tensor([int(hist[int(cuts[k]):int(cuts[k + 1])].sum()) for k in range(world)], dtype=torch.int64)
         return cuts, window_R
 
-    def route_count(self, s, rec, radii, cuts, world):
+    def route_count(self, s, rec, radii, cuts, world, extra=0):
         cover = _tile_cover(rec, radii)
         mask = torch.stack([cover[:, int(cuts[d]):int(cuts[d + 1])].any(1) for d in range(world)], 1)   # [P, G]
-        return mask, mask.sum(0).to(torch.int32)
+        return mask, torch.cat([mask.sum(0).to(torch.int32), torch.tensor([extra], dtype=torch.int32)])
 
     def route_scatter(self, rec, radii, keys, mask, send_counts, n_send, world):
         rows, src = [], []
@@ -81,7 +81,7 @@ class ToyBackend:
             rows.append(row)
             src.append(idx.to(torch.int32))
         rows, src = torch.cat(rows, 0), torch.cat(src, 0)
-        assert rows.shape[0] == n_send == int(send_counts.sum())
+        assert rows.shape[0] == n_send == int(send_counts[:world].sum())
         return rows, src
 
     def unpack(self, rows):

@@ -39,7 +39,7 @@ def main():
         cuts, wr = be.partition(s, hist, G, base)
         cuts_h, wr_h = cuts.cpu().tolist(), wr.cpu().tolist()
         routes = [be.route_count(s, rec, radii, cuts, G) for radii, rec, keys, clamped in pre]
-        cmat = torch.stack([c for _, c in routes]).cpu()
+        cmat = torch.stack([c[:G] for _, c in routes]).cpu()
         print(f"cost_base {base}: cuts {cuts_h}")
         print(f"  rows sent per visible Gaussian: {int(cmat.sum()) / sum(int((p[0] > 0).sum()) for p in pre):.3f}")
         tot_f, tot_b = [], []
