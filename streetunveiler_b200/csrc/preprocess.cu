@@ -13,6 +13,7 @@
 // footprint (ellipse + low-pass disc) used by the render kernels for sub-tile culling.
 #include <cstdio>
 
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -457,7 +458,14 @@ __device__ __forceinline__ float4 quat_vjp(const float4 q, const float vR[3][3])
     return v;
 }
 
-__global__ void __launch_bounds__(256)
+// STAGED (SH rows 16-byte aligned, M <= 16): the three row-shaped streams of a Gaussian -- its 80-B gradient
+// accumulator row, its SH row in and its SH-gradient row out (192 B each at degree 3: two thirds of the kernel's bytes)
+// -- travel through shared memory with the TMA engine: every lane issues ONE bulk copy per row instead of 5 + 12 + 12
+// 128-bit accesses whose 32 lanes touch 32 different cache lines each (ncu r02: the kernel was bound by L1 wavefronts,
+// 23 % issue-active at 56 % of the HBM peak).  Rows are padded by 16 B in shared memory so that the per-lane 128-bit
+// accesses of a quarter warp fall into distinct banks.  The arithmetic is untouched.
+template <bool STAGED>
+__global__ void __launch_bounds__(256, STAGED ? 3 : 1)
 preprocess_bwd_kernel(const int P, const int D, const int M, const float *__restrict__ means3D,
                       const int *__restrict__ radii, const float *__restrict__ shs,
                       const uint8_t *__restrict__ clamped, const float2 *__restrict__ scales,
@@ -471,8 +479,48 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
                       float *__restrict__ dL_dtransMat, float *__restrict__ dL_dsh, float2 *__restrict__ dL_dscale,
                       float4 *__restrict__ dL_drot)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    extern __shared__ __align__(128) unsigned char k8_smem[];
+    const int idx_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!STAGED && idx_raw >= P) return;
+    const bool in_range = idx_raw < P;
+    const int idx = in_range ? idx_raw : P - 1;   // STAGED: lanes past the end keep the warp's barrier protocol, store nothing
+    float *sh_row = nullptr, *g_row = nullptr;
+    // STAGED: the Gaussian's small parameters are fetched while the bulk copies are in flight (one exposed memory
+    // latency instead of a chain of them: the kernel is latency-bound at 2-3 CTAs per SM)
+    float3 pf_p = make_float3(0.f, 0.f, 0.f);
+    float2 pf_sc = make_float2(0.f, 0.f);
+    float4 pf_q = make_float4(0.f, 0.f, 0.f, 1.f);
+    float pf_depth = 0.f;
+    uint32_t pf_cb = 0;
+    if constexpr (STAGED) {
+        const int sh_stride = 3 * M + 4;
+        float *sh_stage = reinterpret_cast<float *>(k8_smem);
+        float *g_stage = sh_stage + 256 * sh_stride;
+        uint64_t *bar = reinterpret_cast<uint64_t *>(g_stage + 256 * GACC_FLOATS) + (threadIdx.x >> 5);
+        sh_row = sh_stage + threadIdx.x * sh_stride;
+        g_row = g_stage + threadIdx.x * GACC_FLOATS;
+        if ((threadIdx.x & 31) == 0) {
+            mbar_init(bar, 32);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        if (in_range && radii[idx] > 0) {
+            const size_t row = gacc_slot ? (size_t)gacc_slot[idx] : (size_t)idx;
+            bulk_g2s(g_row, gacc + row * GACC_FLOATS, GACC_FLOATS * 4, bar);
+            bulk_g2s(sh_row, shs + (size_t)idx * M * 3, (uint32_t)(12 * M), bar);
+            mbar_arrive_expect_tx(bar, (uint32_t)(GACC_FLOATS * 4 + 12 * M));
+            pf_p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+            if (scales != nullptr) {
+                pf_sc = scales[idx];
+                pf_q = rotations[idx];
+            }
+            pf_depth = rec[(size_t)idx * REC_FLOATS + 8];
+            pf_cb = clamped[idx];
+        } else {
+            mbar_arrive_plain(bar);
+        }
+        mbar_wait(bar, 0);
+    }
 
     float o_m2x = 0.f, o_m2y = 0.f, o_op = 0.f;
     float o_col[3] = {0.f, 0.f, 0.f}, o_nrm[3] = {0.f, 0.f, 0.f}, o_m3[3] = {0.f, 0.f, 0.f};
@@ -486,7 +534,7 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
 
     if (visible) {
         const size_t row = gacc_slot ? (size_t)gacc_slot[idx] : (size_t)idx;  // compact rows in the sharded path
-        const float4 *g4 = reinterpret_cast<const float4 *>(gacc + row * GACC_FLOATS);
+        const float4 *g4 = reinterpret_cast<const float4 *>(STAGED ? g_row : gacc + row * GACC_FLOATS);
         const float4 a0 = g4[0], a1 = g4[1], a2 = g4[2], a3 = g4[3], a4 = g4[4];
         float dT[3][3] = {{a0.x, a0.y, a0.z}, {a0.w, a1.x, a1.y}, {a1.z, a1.w, a2.x}};
         float dm2x = a2.y, dm2y = a2.z;
@@ -501,7 +549,7 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
         const int Wb = int(focal_x * tan_fovx * 2);  // backward.cu:613-614 (fp32 round trip, quirk 3)
         const int Hb = int(focal_y * tan_fovy * 2);
         const bool precomp = (scales == nullptr);     // backward.cu:615
-        const float3 p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+        const float3 p_orig = STAGED ? pf_p : make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
 
         float Tm[3][3], Pm[3][4], R[3][3];
         float3 normal = make_float3(0.f, 0.f, 0.f);
@@ -514,8 +562,8 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
                 for (int r = 0; r < 3; r++) Tm[j][r] = transMat_precomp[9 * idx + 3 * j + r];
         } else {
             float L[3][3];
-            sc = scales[idx];
-            q = rotations[idx];
+            sc = STAGED ? pf_sc : scales[idx];
+            q = STAGED ? pf_q : rotations[idx];
             quat_columns(q, R);
             scaled_frame(R, 1.0f * sc.x, 1.0f * sc.y, L);  // scale_modifier ignored (quirk 2)
             const float A[4][3] = {{L[0][0], L[1][0], p_orig.x}, {L[0][1], L[1][1], p_orig.y},
@@ -598,14 +646,14 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
         if (have_sh) {
             const float3 cam = make_float3(cam_pos[0], cam_pos[1], cam_pos[2]);
             dirx = p_orig.x - cam.x; diry = p_orig.y - cam.y; dirz = p_orig.z - cam.z;
-            const uint32_t cb = clamped[idx];
+            const uint32_t cb = STAGED ? pf_cb : (uint32_t)clamped[idx];
 #pragma unroll
             for (int c = 0; c < 3; c++) dRGB[c] = o_col[c] * (((cb >> c) & 1u) ? 0.f : 1.f);
         }
 
         // densification proxy (backward.cu:631-635, quirk 4): uses forward's Tw.z and the
         // (possibly folded, precomp path only) dL_dtransMat
-        const float depth = rec[(size_t)idx * REC_FLOATS + 8];
+        const float depth = STAGED ? pf_depth : rec[(size_t)idx * REC_FLOATS + 8];
         o_m2x = o_T[2] * depth * 0.5 * float(Wb);
         o_m2y = o_T[5] * depth * 0.5 * float(Hb);
     }
@@ -622,7 +670,10 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
                             ((reinterpret_cast<uintptr_t>(shs) & 15) == 0);
         const int nflt = 3 * M;
         if (!visible) {
-            if (vec_ok) {
+            if (STAGED) {
+                float4 *d4 = reinterpret_cast<float4 *>(sh_row);
+                for (int i = 0; i < nflt / 4; i++) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else if (vec_ok) {
                 float4 *d4 = reinterpret_cast<float4 *>(dsh);
                 for (int i = 0; i < nflt / 4; i++) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
@@ -639,7 +690,10 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
                 if (4 * j < nflt) {
                     float v[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
                     if (4 * j < nact) {
-                        if (vec_ok) {
+                        if (STAGED) {
+                            const float4 t = reinterpret_cast<const float4 *>(sh_row)[j];
+                            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                        } else if (vec_ok) {
                             const float4 t = __ldg(reinterpret_cast<const float4 *>(sh) + j);
                             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
                         } else {
@@ -686,7 +740,9 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
                             gz[c] += bz * v[e];
                         }
                     }
-                    if (vec_ok) {
+                    if (STAGED) {
+                        reinterpret_cast<float4 *>(sh_row)[j] = make_float4(o[0], o[1], o[2], o[3]);   // in place: row j was read above
+                    } else if (vec_ok) {
                         reinterpret_cast<float4 *>(dsh)[j] = make_float4(o[0], o[1], o[2], o[3]);
                     } else {
 #pragma unroll
@@ -706,6 +762,11 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
             o_m3[1] += (-dirx * diry * ddx + (sum2 - diry * diry) * ddy - dirz * diry * ddz) * invsum32;
             o_m3[2] += (-dirx * dirz * ddx - diry * dirz * ddy + (sum2 - dirz * dirz) * ddz) * invsum32;
         }
+        if (STAGED && in_range) bulk_s2g(dsh, sh_row, (uint32_t)(12 * M));   // the whole gradient row, one request
+    }
+    if (STAGED && !in_range) {
+        bulk_wait_read_all();
+        return;
     }
 
     dL_dmean2D[3 * idx] = o_m2x;
@@ -722,12 +783,27 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const float *__rest
     for (int i = 0; i < 9; i++) dL_dtransMat[9 * idx + i] = o_T[i];
     dL_dscale[idx] = o_sc;
     dL_drot[idx] = o_rot;
+    if (STAGED) bulk_wait_read_all();   // the staging row must outlive the bulk store's read of it
 }
 
 void launch_preprocess_bwd(const PreprocessBwdArgs &a, cudaStream_t stream)
 {
     if (a.P == 0) return;
-    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(
+    const bool staged = a.shs != nullptr && a.dL_dsh != nullptr && a.M > 0 && a.M <= 16 && (a.M & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(a.shs) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dL_dsh) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(a.gacc) & 15) == 0;
+    if (staged) {
+        const size_t smem = (size_t)256 * (3 * a.M + 4) * 4 + (size_t)256 * GACC_FLOATS * 4 + 8 * sizeof(uint64_t);
+        cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        preprocess_bwd_kernel<true><<<(a.P + 255) / 256, 256, smem, stream>>>(
+            a.P, a.D, a.M, a.means3D, a.radii, a.shs, a.clamped, reinterpret_cast<const float2 *>(a.scales),
+            reinterpret_cast<const float4 *>(a.rotations), a.transMat_precomp, a.viewmatrix, a.projmatrix, a.focal_x,
+            a.focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, a.rec, a.gacc, a.gacc_slot, a.dL_dmean2D, a.dL_dnormal,
+            a.dL_dopacity, a.dL_dcolor, a.dL_dmean3D, a.dL_dtransMat, a.dL_dsh, reinterpret_cast<float2 *>(a.dL_dscale),
+            reinterpret_cast<float4 *>(a.dL_drot));
+        return;
+    }
+    preprocess_bwd_kernel<false><<<(a.P + 255) / 256, 256, 0, stream>>>(
         a.P, a.D, a.M, a.means3D, a.radii, a.shs, a.clamped, reinterpret_cast<const float2 *>(a.scales),
         reinterpret_cast<const float4 *>(a.rotations), a.transMat_precomp, a.viewmatrix, a.projmatrix, a.focal_x,
         a.focal_y, a.tan_fovx, a.tan_fovy, a.cam_pos, a.rec, a.gacc, a.gacc_slot, a.dL_dmean2D, a.dL_dnormal, a.dL_dopacity,
