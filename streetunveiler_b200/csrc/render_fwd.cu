@@ -46,8 +46,13 @@ __device__ __forceinline__ void peer_store(float *p, const float v, const int mu
         *p = v;
 }
 
+#ifdef SURFEL_FWD_MAXREG   // tuning experiments only (tools/gpu_r02_o.sh); the default lets the compiler pick 56 (4 CTAs/SM)
+#define SURFEL_FWD_BOUNDS __maxnreg__(SURFEL_FWD_MAXREG)
+#else
+#define SURFEL_FWD_BOUNDS __launch_bounds__(TILE_THREADS)
+#endif
 template <bool CULL, bool CLASSES, bool PEERS = false>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void SURFEL_FWD_BOUNDS
 render_fwd_kernel(const PeerPlanes peers, const int n_classes,
                   const int W, const int H, const int gx, const uint32_t *__restrict__ tile_order,
                   const uint2 *__restrict__ ranges,
