@@ -480,7 +480,7 @@ SURFEL_API int surfel_debug_copy_geometry(int P, const char *geometry_buffer, ui
  * colour+alpha one.  Synchronises the stream. */
 SURFEL_API int surfel_debug_aux_flag(int P, const char *grad_scratch, int *flag_host, void *stream);
 
-/* Tuning / debug knobs: "subtile_cull" (default 1), "time_stages" (default 0; setting it clears the
+/* Tuning / debug knobs: "radix_onesweep" (default 1; 0 = three-launch radix passes), "bwd_variant", "subtile_cull" (default 1), "time_stages" (default 0; setting it clears the
  * stage clocks).  Returns 0 if the option exists. */
 SURFEL_API int surfel_set_option(const char *name, int value);
 

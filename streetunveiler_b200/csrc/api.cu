@@ -323,6 +323,10 @@ int surfel_set_option(const char *name, int value)
         g_bwd_variant = value;
         return 0;
     }
+    if (name && std::strcmp(name, "radix_onesweep") == 0) {   // 1 (default): one-launch passes with decoupled look-back
+        set_radix_onesweep(value);
+        return 0;
+    }
     if (name && std::strcmp(name, "time_stages") == 0) {  // (re)arms and clears the stage clocks
         std::lock_guard<std::mutex> lock(g_stage_mutex);
         g_time_stages = value;

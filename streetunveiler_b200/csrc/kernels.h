@@ -42,6 +42,7 @@ void launch_preprocess_bwd(const PreprocessBwdArgs &a, cudaStream_t stream);
 
 // ---- radix sort / scan (radix_sort.cu) ----
 size_t radix_sort_temp_bytes(int64_t n);
+void set_radix_onesweep(int v);
 cudaError_t radix_sort_pairs(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
                              int64_t n, int end_bit, char *temp, size_t temp_bytes, cudaStream_t stream);
 size_t scan_temp_bytes(int n);

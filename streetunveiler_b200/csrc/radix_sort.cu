@@ -177,11 +177,184 @@ digit_scatter_kernel(const int64_t n, const uint32_t *__restrict__ keys_in, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-sweep pass (round 2): the three launches of a pass collapse into one.  A prepass reads the keys ONCE and builds
+// the global digit histogram of every pass (the multiset of keys does not change between passes).  The pass kernel
+// then ranks its tile exactly like digit_scatter_kernel and obtains "items with my digit in all earlier tiles" by
+// decoupled look-back over single-word tile descriptors (flag in the top two bits, count below: one relaxed load sees
+// both), instead of reading a [digit][tile] table that a histogram kernel and a row-scan kernel had to produce first.
+// Tiles are handed out by an atomic ticket, so a tile only ever waits for tiles that already run: no deadlock, and
+// tile order = input order, hence the same stable result.  n < 2^30.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t OS_AGG = 1u << 30, OS_PREFIX = 2u << 30, OS_MASK = (1u << 30) - 1u;
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t *p, const uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+digit_histogram_all_kernel(const int64_t n, const uint32_t *__restrict__ keys, const int passes, uint32_t *__restrict__ ghist)
+{
+    __shared__ uint32_t h[4][256];
+    for (int i = threadIdx.x; i < 4 * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RS_THREADS) {
+        const uint32_t k = keys[i];
+        for (int p = 0; p < passes; p++) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += RS_THREADS) {
+        const uint32_t v = (&h[0][0])[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+onesweep_pass_kernel(const int64_t n, const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const int shift,
+                     const uint32_t *__restrict__ ghist, uint32_t *__restrict__ desc, uint32_t *__restrict__ ticket)
+{
+    __shared__ uint32_t wcnt[RS_WARPS][256];   // per-warp running digit counts -> exclusive bases across warps
+    __shared__ uint32_t gbase[256];            // global offset of (digit, this tile)
+    __shared__ uint32_t wsum[RS_WARPS];
+    __shared__ uint32_t dstart[256];           // start of each digit's run in tile-sorted order
+    __shared__ uint32_t s_k[RS_TILE], s_v[RS_TILE];
+    __shared__ uint32_t s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) wcnt[w][threadIdx.x] = 0;
+    uint32_t digit_start;
+    {   // exclusive scan of the 256 global digit totals (thread = digit): where each digit's run starts
+        const uint32_t t = ghist[threadIdx.x];
+        uint32_t x = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += wsum[w];
+        digit_start = wb + x - t;
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+
+    const int64_t wbase = (int64_t)tile * RS_TILE + (int64_t)warp * RS_WARP_SPAN;
+    uint32_t k[RS_ROUNDS], v[RS_ROUNDS], rank[RS_ROUNDS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        const int64_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        k[r] = ok ? keys_in[i] : 0xffffffffu;
+        v[r] = ok ? vals_in[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        const int64_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = (k[r] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : (256u + lane));
+        const uint32_t before = wcnt[warp][d];
+        rank[r] = before + __popc(peers & lt);
+        __syncwarp();
+        if (ok && (peers & lt) == 0u) wcnt[warp][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            const uint32_t c = wcnt[w][threadIdx.x];
+            wcnt[w][threadIdx.x] = run;
+            run += c;
+        }
+        // publish this tile's count of digit `threadIdx.x`, then look back over the earlier tiles
+        uint32_t *mine = desc + (size_t)tile * 256 + threadIdx.x;
+        st_relaxed(mine, (tile == 0 ? OS_PREFIX : OS_AGG) | run);
+        uint32_t excl = 0;
+        if (tile > 0) {
+            // eight predecessors per round trip (independent loads); a descriptor that is not published yet ends the
+            // batch and is asked for again
+            int64_t p = (int64_t)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t d[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    d[u] = (p - u >= 0) ? ld_relaxed(desc + (size_t)(p - u) * 256 + threadIdx.x) : OS_PREFIX;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (done) break;
+                    if ((d[u] >> 30) == 0u) break;          // not there yet: retry from this tile
+                    excl += d[u] & OS_MASK;
+                    p--;
+                    if ((d[u] >> 30) == 2u) done = true;
+                }
+            }
+            st_relaxed(mine, OS_PREFIX | (excl + run));
+        }
+        gbase[threadIdx.x] = digit_start + excl;
+        uint32_t x = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += wsum[w];
+        dstart[threadIdx.x] = wb + x - run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        const int64_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (k[r] >> shift) & 255u;
+            const uint32_t lpos = dstart[d] + wcnt[warp][d] + rank[r];
+            s_k[lpos] = k[r];
+            s_v[lpos] = v[r];
+        }
+    }
+    __syncthreads();
+    const int64_t tile_base = (int64_t)tile * RS_TILE;
+    const int nvalid = (int)((n - tile_base) < (int64_t)RS_TILE ? (n - tile_base) : (int64_t)RS_TILE);
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; r++) {
+        const int lp = r * RS_THREADS + threadIdx.x;
+        if (lp < nvalid) {
+            const uint32_t kk = s_k[lp];
+            const uint32_t d = (kk >> shift) & 255u;
+            const uint32_t pos = gbase[d] + ((uint32_t)lp - dstart[d]);
+            keys_out[pos] = kk;
+            vals_out[pos] = s_v[lp];
+        }
+    }
+}
+
+int g_radix_onesweep = 1;   // surfel_set_option("radix_onesweep", 0) selects the three-launch passes (debugging / tests)
+void set_radix_onesweep(int v) { g_radix_onesweep = v; }
+
 size_t radix_sort_temp_bytes(int64_t n)
 {
     const int64_t nblocks = (n + RS_TILE - 1) / RS_TILE;
-    // hist [256][nblocks] + totals [256] + ping-pong keys/vals for the intermediate passes
-    return (size_t)(256 * (nblocks > 0 ? nblocks : 1) + 256) * sizeof(uint32_t) + 2 * (size_t)(n > 0 ? n : 1) * sizeof(uint32_t) + 512;
+    // hist [256][nblocks] (or tile descriptors [nblocks][256]) + totals [256] (or the ticket) + global histograms
+    // [4][256] + ping-pong keys/vals for the intermediate passes
+    return (size_t)(256 * (nblocks > 0 ? nblocks : 1) + 256 + 4 * 256) * sizeof(uint32_t) +
+           2 * (size_t)(n > 0 ? n : 1) * sizeof(uint32_t) + 1024;
 }
 
 // Stable sort of n pairs on key bits [0, end_bit).  Result in (keys_out, vals_out).  The inputs are
@@ -197,17 +370,33 @@ cudaError_t radix_sort_pairs(const uint32_t *keys_in, const uint32_t *vals_in, u
     char *p = temp;
     uint32_t *hist = carve<uint32_t>(p, (size_t)256 * nblocks);
     uint32_t *totals = carve<uint32_t>(p, 256);
+    uint32_t *ghist = carve<uint32_t>(p, 4 * 256);
     uint32_t *keys_tmp = carve<uint32_t>(p, (size_t)n);
     uint32_t *vals_tmp = carve<uint32_t>(p, (size_t)n);
+    const bool onesweep = g_radix_onesweep != 0 && n < (int64_t(1) << 30) && passes <= 4;
+    if (onesweep) {
+        cudaError_t e = cudaMemsetAsync(ghist, 0, 4 * 256 * sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+        const int grid = nblocks < 148 * 4 ? nblocks : 148 * 4;
+        digit_histogram_all_kernel<<<grid, RS_THREADS, 0, stream>>>(n, keys_in, passes, ghist);
+    }
     // choose the ping-pong so that the LAST pass writes (keys_out, vals_out)
     const uint32_t *src_k = keys_in, *src_v = vals_in;
     for (int pass = 0; pass < passes; pass++) {
         const bool to_out = ((passes - 1 - pass) % 2) == 0;
         uint32_t *dst_k = to_out ? keys_out : keys_tmp, *dst_v = to_out ? vals_out : vals_tmp;
         const int shift = 8 * pass;
-        digit_histogram_kernel<<<nblocks, RS_THREADS, 0, stream>>>(n, src_k, shift, nblocks, hist);
-        digit_row_scan_kernel<<<256, 256, 0, stream>>>(nblocks, hist, totals);
-        digit_scatter_kernel<<<nblocks, RS_THREADS, 0, stream>>>(n, src_k, src_v, dst_k, dst_v, shift, nblocks, hist, totals);
+        if (onesweep) {
+            // descriptors [nblocks][256] and the ticket (first word of `totals`, adjacent) are cleared per pass
+            cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)((char *)(totals + 256) - (char *)hist), stream);
+            if (e != cudaSuccess) return e;
+            onesweep_pass_kernel<<<nblocks, RS_THREADS, 0, stream>>>(n, src_k, src_v, dst_k, dst_v, shift, ghist + 256 * pass,
+                                                                     hist, totals);
+        } else {
+            digit_histogram_kernel<<<nblocks, RS_THREADS, 0, stream>>>(n, src_k, shift, nblocks, hist);
+            digit_row_scan_kernel<<<256, 256, 0, stream>>>(nblocks, hist, totals);
+            digit_scatter_kernel<<<nblocks, RS_THREADS, 0, stream>>>(n, src_k, src_v, dst_k, dst_v, shift, nblocks, hist, totals);
+        }
         src_k = dst_k;
         src_v = dst_v;
     }

@@ -247,9 +247,12 @@ def test_shard_compaction_keeps_index_order(P, frac):
     assert torch.equal(slot.cpu(), want)
 
 
-@pytest.mark.parametrize("n,bits", [(1, 8), (33, 14), (2048, 14), (2049, 32), (300_001, 14), (1_000_003, 32), (5_500_000, 14)])
-def test_radix_sort_is_a_stable_sort(n, bits):
-    """The hand-written LSD radix sort (csrc/radix_sort.cu) against torch's stable sort: bit-exact."""
+@pytest.mark.parametrize("onesweep", [1, 0])
+@pytest.mark.parametrize("n,bits", [(1, 8), (33, 14), (2048, 14), (2049, 32), (300_001, 14), (1_000_003, 32), (5_500_000, 14),
+                                    (8_000_000, 32)])
+def test_radix_sort_is_a_stable_sort(n, bits, onesweep):
+    """The hand-written LSD radix sort (csrc/radix_sort.cu) against torch's stable sort: bit-exact -- both the one-sweep
+    passes (decoupled look-back, the default) and the three-launch passes."""
     import ctypes as C
     from streetunveiler_b200 import _lib
     dev = torch.device("cuda")
@@ -266,8 +269,14 @@ def test_radix_sort_is_a_stable_sort(n, bits):
     vin = vals.to(torch.int32).to(dev)
     kout, vout = torch.empty_like(kin), torch.empty_like(vin)
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-    _lib.check(_lib.lib().surfel_debug_sort_pairs(n, bits, p(kin), p(vin), p(kout), p(vout),
-                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sort")
+    _lib.set_option("radix_onesweep", onesweep)
+    try:
+        for _ in range(3 if n > 1_000_000 else 1):      # repeated: the look-back depends on CTA timing
+            kout.fill_(0)
+            _lib.check(_lib.lib().surfel_debug_sort_pairs(n, bits, p(kin), p(vin), p(kout), p(vout),
+                                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sort")
+    finally:
+        _lib.set_option("radix_onesweep", 1)
     order = torch.sort(keys, stable=True)[1]
     assert torch.equal(vout.cpu().to(torch.int64), order)
     assert torch.equal(kout.cpu().to(torch.int64) & 0xFFFFFFFF, keys[order])
