@@ -675,7 +675,6 @@ def run_ours(args):
         info = _shm.LAST_INFO
         if info.get("send"):
             snd, rcv = info["send"], info["recv"]
-            own = world and rank
             out_rows = sum(snd) - snd[rank]
             back_rows = sum(rcv) - rcv[rank]
             HW_ = wl.cam.width * wl.cam.height

@@ -12,6 +12,8 @@
 // Order among equal digits = (cta, warp, round, lane) = input order, so every pass is stable and the
 // composition over passes is a stable sort on the selected key bits (what the reference relies on for
 // equal (tile, depth) keys).
+#include <atomic>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -345,8 +347,8 @@ onesweep_pass_kernel(const int64_t n, const uint32_t *__restrict__ keys_in, cons
     }
 }
 
-int g_radix_onesweep = 1;   // surfel_set_option("radix_onesweep", 0) selects the three-launch passes (debugging / tests)
-void set_radix_onesweep(int v) { g_radix_onesweep = v; }
+std::atomic<int> g_radix_onesweep{1};   // surfel_set_option("radix_onesweep", 0): three-launch passes (debugging / tests)
+void set_radix_onesweep(int v) { g_radix_onesweep.store(v, std::memory_order_relaxed); }
 
 size_t radix_sort_temp_bytes(int64_t n)
 {
@@ -373,7 +375,7 @@ cudaError_t radix_sort_pairs(const uint32_t *keys_in, const uint32_t *vals_in, u
     uint32_t *ghist = carve<uint32_t>(p, 4 * 256);
     uint32_t *keys_tmp = carve<uint32_t>(p, (size_t)n);
     uint32_t *vals_tmp = carve<uint32_t>(p, (size_t)n);
-    const bool onesweep = g_radix_onesweep != 0 && n < (int64_t(1) << 30) && passes <= 4;
+    const bool onesweep = g_radix_onesweep.load(std::memory_order_relaxed) != 0 && n < (int64_t(1) << 30) && passes <= 4;
     if (onesweep) {
         cudaError_t e = cudaMemsetAsync(ghist, 0, 4 * 256 * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return e;
